@@ -1,0 +1,154 @@
+/*
+ * qcs_cuda.h -- extern "C" ABI of libqcs_cuda.so, the sm_100a state-vector
+ * engine behind the QCS_GPU_CUDA mode of include/qcs.h.
+ *
+ * This is the drop-in boundary: plain pointers, ints, longs and doubles only
+ * (C89-callable; no CUDA, C++ or torch types).  Each entry point replaces one
+ * host-side touch of `state->vector` in the reference; the reference file:line
+ * it stands in for is cited beside it.  The reference's own GPU seam has the
+ * same shape -- `q_apply_1q_gate_gpu(state, gate, target)` and
+ * `q_apply_2q_gate_gpu(state, gate, control, target)` (reference
+ * src/q_gates.c:13-17, called at :39 and :173) -- but it leaves every other
+ * read of the state on the host; this ABI moves all of them to the device.
+ *
+ * Conventions
+ *   - qubit q is bit q of the basis index (reference src/q_gates.c:28).
+ *   - a 2x2 gate is `const double m[8]`: row-major U00,U01,U10,U11, each
+ *     {re, im} (reference src/q_gates.c:140-141).  It is copied at call time.
+ *   - every function returns 0 on success, non-zero on error;
+ *     qcs_cuda_last_error() then describes it.  Nothing falls back to the CPU.
+ *   - gate calls are deferred into a fusion queue; any call that returns data
+ *     (or qcs_cuda_flush) executes the queue first, so results are
+ *     observationally identical to eager application.
+ *   - not thread-safe per engine; several engines may coexist.
+ */
+#ifndef QCS_CUDA_H
+#define QCS_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qcs_cuda_engine qcs_cuda_engine;
+
+enum {
+  QCS_CUDA_OK = 0,
+  QCS_CUDA_ERR_INVALID = 1, /* bad qubit / index; state untouched           */
+  QCS_CUDA_ERR_CUDA = 2,    /* CUDA runtime / driver failure                */
+  QCS_CUDA_ERR_NOMEM = 3,   /* device allocation failed                     */
+  QCS_CUDA_ERR_NCCL = 4,    /* communicator failure                         */
+  QCS_CUDA_ERR_DRYRUN = 5   /* data requested from a plan-only engine       */
+};
+
+/* ---- storage: q_state_init / q_state_free (reference src/q_state.c:32-115) -- */
+/* Allocates the device-resident amplitude buffer(s), zeroes them and sets
+ * amplitude 0 to 1.  With a communicator installed (qcs_cuda_dist_init) the
+ * state is sharded on its top log2(world) qubits and this rank holds one shard. */
+int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits);
+void qcs_cuda_state_destroy(qcs_cuda_engine *e);
+
+/* ---- gates ----------------------------------------------------------------- */
+/* q_apply_1q_gate (reference src/q_gates.c:25-149). */
+int qcs_cuda_apply_1q(qcs_cuda_engine *e, const double m[8], int target);
+/* q_apply_2q_gate, controlled 2x2 (reference src/q_gates.c:158-298). */
+int qcs_cuda_apply_c1q(qcs_cuda_engine *e, const double m[8], int control,
+                       int target);
+/* q_apply_phase_flip (reference src/q_gates.c:305-317). */
+int qcs_cuda_phase_flip(qcs_cuda_engine *e, long index);
+/* q_apply_diffusion (reference src/q_gates.c:323-356). */
+int qcs_cuda_diffusion(qcs_cuda_engine *e);
+/* q_state_normalize (reference src/q_utils.c:44-119). */
+int qcs_cuda_normalize(qcs_cuda_engine *e);
+
+/* ---- measurement: the loops of qc_measure (reference src/qcs.c:237-284) ---- */
+/* prob_0 = sum over basis states with bit `qubit` clear, accumulated in
+ * ascending index order (reference src/qcs.c:253-259); the device result is
+ * the sequentially rounded sum, bit for bit. */
+int qcs_cuda_prob0(qcs_cuda_engine *e, int qubit, double *p0);
+/* Zeroes the amplitudes with bit `qubit` != outcome, then normalises
+ * (reference src/qcs.c:264-281). */
+int qcs_cuda_collapse(qcs_cuda_engine *e, int qubit, int outcome);
+
+/* ---- state access ------------------------------------------------------------ */
+/* state->vector[index] (reference src/q_state.c:145-165). */
+int qcs_cuda_get_amplitude(qcs_cuda_engine *e, long index, double out[2]);
+/* c_norm_sq(state->vector[index]) (reference src/qcs.c:391-395); out-of-range
+ * index yields 0.0 and returns QCS_CUDA_OK like the reference. */
+int qcs_cuda_probability(qcs_cuda_engine *e, long index, double *p);
+/* First strict maximum of |a|^2, all-zero state -> 0 (reference src/qcs.c:464-478). */
+int qcs_cuda_argmax(qcs_cuda_engine *e, long *index);
+
+/* ---- sampling: the shot loop of qc_run_shots (reference src/qcs.c:589-605) -- */
+/* For each u[k] (= rand()/(double)RAND_MAX drawn by the host in shot order)
+ * writes the smallest basis index i with u[k] < p_0 (+) p_1 (+) ... (+) p_i,
+ * (+) being the reference's left-to-right rounded accumulation, or -1 when no
+ * such i exists (the reference drops that shot). */
+int qcs_cuda_sample(qcs_cuda_engine *e, const double *u, int shots,
+                    long *indices);
+
+/* ---- queue / bulk transfer ----------------------------------------------------- */
+int qcs_cuda_flush(qcs_cuda_engine *e);
+/* Copies `count` amplitudes starting at basis index `first` to/from host
+ * memory as interleaved {re,im} doubles.  which = 0: live buffer
+ * (state->vector), 1: scratch buffer (state->scratch_vector; only maintained
+ * under reference semantics).  Used by qc_print_state and by
+ * the parity tests. */
+int qcs_cuda_read_amplitudes(qcs_cuda_engine *e, int which, long first,
+                             long count, double *out);
+int qcs_cuda_write_amplitudes(qcs_cuda_engine *e, int which, long first,
+                              long count, const double *in);
+
+/* ---- configuration / introspection ------------------------------------------------ */
+/* Keys: "semantics" = reference|corrected, "fusion" = on|off,
+ * "dryrun" = 0|1, "pass_flops" = <int>, "tile_kernel" = ldg|tma.
+ * Defaults come from QCS_CUDA_<KEY> in the environment; set_default applies
+ * to engines created afterwards. */
+int qcs_cuda_set_default(const char *key, const char *value);
+int qcs_cuda_num_qubits(const qcs_cuda_engine *e);
+
+typedef struct qcs_cuda_stats {
+  long gates_submitted;     /* qcs_cuda_apply_* calls accepted            */
+  long gates_executed;         /* gates that reached a kernel                */
+  long passes;                 /* fused tile-kernel launches                 */
+  long kernel_launches;        /* every kernel this library launched         */
+  long segments;               /* in-tile register re-assignments            */
+  long remaps;                 /* global<->local qubit exchanges             */
+  double algorithmic_bytes;    /* SURVEY 8(d) bytes of all executed passes   */
+  double pass_bytes;           /* same, fused tile passes only               */
+  double pass_ms;              /* device time inside fused tile passes       */
+  double exchange_bytes;       /* bytes sent over NVLink by this rank        */
+  double exchange_ms;          /* device time inside exchanges               */
+} qcs_cuda_stats;
+
+int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out);
+int qcs_cuda_reset_stats(qcs_cuda_engine *e);
+/* When enabled (non-zero) every fused pass is bracketed by CUDA events on the
+ * engine's stream so pass_ms is filled in (used by bench.py's roofline). */
+int qcs_cuda_set_timing(qcs_cuda_engine *e, int enabled);
+
+/* Writes a human-readable description of the passes the last flush executed
+ * (tile bits, segments, gates per segment) into buf; returns bytes needed. */
+long qcs_cuda_describe_last_plan(qcs_cuda_engine *e, char *buf, long cap);
+
+const char *qcs_cuda_last_error(void);
+
+/* ---- multi-GPU (one process per GPU; NCCL over NVLink) ---------------------------- */
+/* Rank 0 obtains an id, the launcher broadcasts the 128 bytes (bench.py uses
+ * torch.distributed), then every rank calls qcs_cuda_dist_init.  Engines
+ * created afterwards are shards of one logical state. */
+int qcs_cuda_dist_unique_id(char id[128]);
+int qcs_cuda_dist_init(int rank, int world, const char id[128], int device);
+int qcs_cuda_dist_finalize(void);
+int qcs_cuda_dist_rank(void);
+int qcs_cuda_dist_world(void);
+
+/* Exported by the host layer (libqcs.so), not by libqcs_cuda.so: the engine
+ * behind a circuit, for callers that want the bulk-transfer / statistics entry
+ * points above next to the qcs.h API (tests, bench.py). */
+struct t_q_circuit;
+qcs_cuda_engine *qc_cuda_engine(struct t_q_circuit *circuit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCS_CUDA_H */

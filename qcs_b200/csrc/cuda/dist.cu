@@ -1,0 +1,262 @@
+// dist.cu -- multi-GPU plumbing: one process per GPU, NCCL over NVLink 5.
+//
+// The reference has no multi-process mode at all; this
+// is the sharding the north star asks for: rank r owns the amplitudes whose top
+// log2(P) physical index bits equal r.  Diagonal gates and controls on a global
+// position need no communication.  A pairing gate whose target sits on a global
+// position g is made local by SWAPPING physical positions g and a local
+// position l: each rank keeps the half of its shard whose bit l equals its own
+// g-bit and trades the other half with partner rank ^ (1 << (g - nl)).  Half a
+// shard crosses NVLink in each direction (8 * 2^nl bytes per rank per
+// direction), after which the engine's logical->physical permutation records
+// the new layout and every later gate on that qubit is local.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library itself is dlopen'ed
+
+#include <cstring>
+#include <vector>
+
+#include "../../../include/qcs_cuda.h"
+#include "engine.h"
+
+namespace qcs {
+
+DistContext &dist() {
+  static DistContext d;
+  return d;
+}
+
+// NCCL is bound at run time, not at link time: a process that also hosts
+// PyTorch must end up with ONE libnccl.so.2 (torch's bundled copy), and a
+// single-GPU user should not need NCCL installed at all.  dlopen by SONAME
+// returns the copy already in the process if there is one.
+namespace nccl_api {
+#define QCS_NCCL_FUNCS(X)                                                              \
+  X(ncclGetUniqueId) X(ncclCommInitRank) X(ncclCommDestroy) X(ncclGetErrorString)      \
+  X(ncclGroupStart) X(ncclGroupEnd) X(ncclSend) X(ncclRecv) X(ncclAllReduce)           \
+  X(ncclAllGather)
+#define X(name) static decltype(&::name) qn_##name = nullptr;
+QCS_NCCL_FUNCS(X)
+#undef X
+static bool loaded = false;
+static int load() {
+  if (loaded) return QCS_CUDA_OK;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!h) return set_error(QCS_CUDA_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define X(name)                                                                        \
+  qn_##name = (decltype(&::name))dlsym(h, #name);                                      \
+  if (!qn_##name) return set_error(QCS_CUDA_ERR_NCCL, "libnccl lacks %s", #name);
+  QCS_NCCL_FUNCS(X)
+#undef X
+  loaded = true;
+  return QCS_CUDA_OK;
+}
+}  // namespace nccl_api
+// From here on the NCCL names resolve to the run-time bound pointers.
+#define ncclGetUniqueId nccl_api::qn_ncclGetUniqueId
+#define ncclCommInitRank nccl_api::qn_ncclCommInitRank
+#define ncclCommDestroy nccl_api::qn_ncclCommDestroy
+#define ncclGetErrorString nccl_api::qn_ncclGetErrorString
+#define ncclGroupStart nccl_api::qn_ncclGroupStart
+#define ncclGroupEnd nccl_api::qn_ncclGroupEnd
+#define ncclSend nccl_api::qn_ncclSend
+#define ncclRecv nccl_api::qn_ncclRecv
+#define ncclAllReduce nccl_api::qn_ncclAllReduce
+#define ncclAllGather nccl_api::qn_ncclAllGather
+
+static void *g_small_dev = nullptr;  // scratch for host-visible small collectives
+static const size_t kSmallBytes = 1 << 20;
+
+static int check_nccl(ncclResult_t r, const char *what) {
+  if (r == ncclSuccess) return QCS_CUDA_OK;
+  return set_error(QCS_CUDA_ERR_NCCL, "%s: %s", what, ncclGetErrorString(r));
+}
+#define NK(call)                              \
+  do {                                        \
+    int rc_ = check_nccl((call), #call);      \
+    if (rc_ != QCS_CUDA_OK) return rc_;       \
+  } while (0)
+#define CK(call)                              \
+  do {                                        \
+    int rc_ = check_cuda((call), #call);      \
+    if (rc_ != QCS_CUDA_OK) return rc_;       \
+  } while (0)
+
+namespace {
+
+// staging[j] = live[expand(j)] (pack) or the reverse (unpack), where expand
+// inserts bit value `bitval` at position `pos`.
+__global__ void __launch_bounds__(256)
+pack_half_kernel(const double2 *__restrict__ live, double2 *__restrict__ staging, uint64_t n_half,
+                 int pos, uint64_t bitval) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_half; j += stride) {
+    const uint64_t low = j & ((1ull << pos) - 1ull);
+    const uint64_t i = (((j >> pos) << (pos + 1)) | low) | (bitval << pos);
+    __stcs(staging + j, __ldcs(live + i));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_half_kernel(double2 *__restrict__ live, const double2 *__restrict__ staging,
+                   uint64_t n_half, int pos, uint64_t bitval) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_half; j += stride) {
+    const uint64_t low = j & ((1ull << pos) - 1ull);
+    const uint64_t i = (((j >> pos) << (pos + 1)) | low) | (bitval << pos);
+    __stcs(live + i, __ldcs(staging + j));
+  }
+}
+
+}  // namespace
+
+int dist_swap_positions(Engine &e, int lpos, int gpos) {
+  DistContext &d = dist();
+  if (!d.active) return set_error(QCS_CUDA_ERR_INVALID, "global position without a communicator");
+  ncclComm_t comm = (ncclComm_t)d.comm;
+  const int gbit = gpos - e.nl;
+  const int partner = d.rank ^ (1 << gbit);
+  const uint64_t mybit = (uint64_t)((d.rank >> gbit) & 1);
+  const uint64_t leaving = 1ull - mybit;  // the half whose bit lpos differs from my g-bit leaves
+  const uint64_t n_half = e.local_size >> 1;
+  const size_t half_bytes = n_half * sizeof(double2);
+  if (!e.staging) CK(cudaMalloc(&e.staging, 2 * half_bytes));
+  double2 *send_buf = e.staging;
+  double2 *recv_buf = e.staging + n_half;
+
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (e.timing) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, e.stream);
+  }
+  const bool contiguous = (lpos == e.nl - 1);
+  const double2 *src = send_buf;
+  if (contiguous) {
+    src = e.live + leaving * n_half;  // the leaving half is one contiguous range
+  } else {
+    pack_half_kernel<<<148 * 8, 256, 0, e.stream>>>(e.live, send_buf, n_half, lpos, leaving);
+    CK(cudaGetLastError());
+    e.kernel_launches++;
+  }
+  NK(ncclGroupStart());
+  NK(ncclSend(src, half_bytes, ncclChar, partner, comm, e.stream));
+  NK(ncclRecv(recv_buf, half_bytes, ncclChar, partner, comm, e.stream));
+  NK(ncclGroupEnd());
+  if (contiguous) {
+    CK(cudaMemcpyAsync(e.live + leaving * n_half, recv_buf, half_bytes, cudaMemcpyDeviceToDevice,
+                       e.stream));
+  } else {
+    unpack_half_kernel<<<148 * 8, 256, 0, e.stream>>>(e.live, recv_buf, n_half, lpos, leaving);
+    CK(cudaGetLastError());
+    e.kernel_launches++;
+  }
+  if (ev0) {
+    cudaEventRecord(ev1, e.stream);
+    e.pending_xchg_events.emplace_back(ev0, ev1);
+  }
+  return QCS_CUDA_OK;
+}
+
+int dist_allreduce_sum(Engine &e, double *dev_values, int count) {
+  DistContext &d = dist();
+  if (!d.active) return QCS_CUDA_OK;
+  NK(ncclAllReduce(dev_values, dev_values, count, ncclDouble, ncclSum, (ncclComm_t)d.comm,
+                   e.stream));
+  return QCS_CUDA_OK;
+}
+
+int dist_allreduce_max_i64(Engine &e, long long *dev_values, size_t count) {
+  DistContext &d = dist();
+  if (!d.active) return QCS_CUDA_OK;
+  NK(ncclAllReduce(dev_values, dev_values, count, ncclInt64, ncclMax, (ncclComm_t)d.comm,
+                   e.stream));
+  return QCS_CUDA_OK;
+}
+
+int dist_allgather_host(const void *mine, void *all, size_t bytes_each) {
+  DistContext &d = dist();
+  if (!d.active) {
+    std::memcpy(all, mine, bytes_each);
+    return QCS_CUDA_OK;
+  }
+  if (bytes_each * (size_t)(d.world + 1) > kSmallBytes)
+    return set_error(QCS_CUDA_ERR_INVALID, "dist_allgather_host: payload too large");
+  char *dev = (char *)g_small_dev;
+  char *dev_all = dev + bytes_each;
+  CK(cudaMemcpy(dev, mine, bytes_each, cudaMemcpyHostToDevice));
+  NK(ncclAllGather(dev, dev_all, bytes_each, ncclChar, (ncclComm_t)d.comm, 0));
+  CK(cudaStreamSynchronize(0));
+  CK(cudaMemcpy(all, dev_all, bytes_each * d.world, cudaMemcpyDeviceToHost));
+  return QCS_CUDA_OK;
+}
+
+int dist_barrier(Engine &e) {
+  double dummy = 0.0;
+  std::vector<double> all(dist().world > 0 ? dist().world : 1);
+  (void)e;
+  return dist_allgather_host(&dummy, all.data(), sizeof(double));
+}
+
+}  // namespace qcs
+
+using namespace qcs;
+
+extern "C" {
+
+int qcs_cuda_dist_unique_id(char id[128]) {
+  static_assert(NCCL_UNIQUE_ID_BYTES == 128, "unique id size");
+  ncclUniqueId uid;
+  int rc = nccl_api::load();
+  if (rc) return rc;
+  rc = check_nccl(ncclGetUniqueId(&uid), "ncclGetUniqueId");
+  if (rc) return rc;
+  std::memcpy(id, &uid, 128);
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_dist_init(int rank, int world, const char id[128], int device) {
+  DistContext &d = dist();
+  if (d.active) return set_error(QCS_CUDA_ERR_INVALID, "communicator already initialised");
+  if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world)
+    return set_error(QCS_CUDA_ERR_INVALID, "world size must be a power of two (got %d)", world);
+  int rc = nccl_api::load();
+  if (rc) return rc;
+  rc = check_cuda(cudaSetDevice(device), "cudaSetDevice");
+  if (rc) return rc;
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, 128);
+  ncclComm_t comm = nullptr;
+  rc = check_nccl(ncclCommInitRank(&comm, world, uid, rank), "ncclCommInitRank");
+  if (rc) return rc;
+  rc = check_cuda(cudaMalloc(&g_small_dev, kSmallBytes), "cudaMalloc(small)");
+  if (rc) return rc;
+  d.comm = comm;
+  d.rank = rank;
+  d.world = world;
+  d.device = device;
+  d.rank_bits = 0;
+  while ((1 << d.rank_bits) < world) d.rank_bits++;
+  d.active = world > 1;
+  if (!d.active) {  // single rank: behave exactly like the non-distributed engine
+    ncclCommDestroy(comm);
+    d.comm = nullptr;
+  }
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_dist_finalize(void) {
+  DistContext &d = dist();
+  if (d.comm) ncclCommDestroy((ncclComm_t)d.comm);
+  if (g_small_dev) cudaFree(g_small_dev);
+  g_small_dev = nullptr;
+  d = DistContext();
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_dist_rank(void) { return dist().active ? dist().rank : 0; }
+int qcs_cuda_dist_world(void) { return dist().active ? dist().world : 1; }
+
+}  // extern "C"

@@ -1,0 +1,800 @@
+// engine.cu -- the extern "C" ABI of include/qcs_cuda.h: device-resident state,
+// deferred gate queue, flush through the fusion planner, measurement and
+// sampling.  Everything the reference does on the host with state->vector
+// (SURVEY.md section 8b lists the sites) funnels through here.
+#include "engine.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+
+#include "../../../include/qcs_cuda.h"
+
+namespace qcs {
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_error[512] = "";
+
+int set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  std::vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return QCS_CUDA_OK;
+  return set_error(e == cudaErrorMemoryAllocation ? QCS_CUDA_ERR_NOMEM : QCS_CUDA_ERR_CUDA,
+                   "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CK(call)                                   \
+  do {                                             \
+    int rc_ = check_cuda((call), #call);           \
+    if (rc_ != QCS_CUDA_OK) return rc_;            \
+  } while (0)
+#define RC(call)                                   \
+  do {                                             \
+    int rc_ = (call);                              \
+    if (rc_ != QCS_CUDA_OK) return rc_;            \
+  } while (0)
+
+// ------------------------------------------------------------------ options
+static std::map<std::string, std::string> &defaults() {
+  static std::map<std::string, std::string> d;
+  return d;
+}
+
+static std::string option_value(const char *key) {
+  auto it = defaults().find(key);
+  if (it != defaults().end()) return it->second;
+  std::string env = "QCS_CUDA_";
+  for (const char *p = key; *p; p++) env += (char)toupper(*p);
+  const char *v = std::getenv(env.c_str());
+  return v ? std::string(v) : std::string();
+}
+
+static int load_options(Options &o) {
+  std::string v = option_value("semantics");
+  if (v == "corrected") o.sem = SEM_CORRECTED;
+  else if (v.empty() || v == "reference") o.sem = SEM_REFERENCE;
+  else return set_error(QCS_CUDA_ERR_INVALID, "semantics must be reference|corrected, got '%s'", v.c_str());
+  v = option_value("fusion");
+  if (v == "off" || v == "0") o.fusion = false;
+  else if (v.empty() || v == "on" || v == "1") o.fusion = true;
+  else return set_error(QCS_CUDA_ERR_INVALID, "fusion must be on|off, got '%s'", v.c_str());
+  v = option_value("dryrun");
+  o.dryrun = (v == "1" || v == "on");
+  v = option_value("pass_flops");
+  if (!v.empty()) o.pass_flops = std::atof(v.c_str());
+  if (!(o.pass_flops > 0)) o.pass_flops = 96.0;
+  v = option_value("tile_kernel");
+  if (v == "ldg") o.tile_kernel = 0;
+  else if (v == "tma16") o.tile_kernel = 1;
+  else if (v.empty() || v == "tma" || v == "tma8") o.tile_kernel = 2;
+  else return set_error(QCS_CUDA_ERR_INVALID, "tile_kernel must be ldg|tma|tma16, got '%s'", v.c_str());
+  v = option_value("exchange");
+  o.exchange = (v == "p2p") ? 1 : 0;
+  return QCS_CUDA_OK;
+}
+
+// ------------------------------------------------------------------ events / stats
+static cudaEvent_t get_event(Engine &e) {
+  if (!e.event_pool.empty()) {
+    cudaEvent_t ev = e.event_pool.back();
+    e.event_pool.pop_back();
+    return ev;
+  }
+  cudaEvent_t ev = nullptr;
+  cudaEventCreate(&ev);
+  return ev;
+}
+
+static void fold_events(Engine &e) {
+  if (e.pending_pass_events.empty() && e.pending_xchg_events.empty()) return;
+  cudaStreamSynchronize(e.stream);
+  for (auto &pr : e.pending_pass_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) e.pass_ms += ms;
+    e.event_pool.push_back(pr.first);
+    e.event_pool.push_back(pr.second);
+  }
+  e.pending_pass_events.clear();
+  for (auto &pr : e.pending_xchg_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) e.exchange_ms += ms;
+    e.event_pool.push_back(pr.first);
+    e.event_pool.push_back(pr.second);
+  }
+  e.pending_xchg_events.clear();
+}
+
+// ------------------------------------------------------------------ scratch buffer
+static int ensure_scratch(Engine &e) {
+  if (e.scratch || e.opt.dryrun) return QCS_CUDA_OK;
+  CK(cudaMalloc(&e.scratch, e.local_size * sizeof(double2)));
+  // q_state_init zeroes both buffers (reference src/q_state.c:93-96)
+  CK(launch_init_state(e.scratch, e.local_size, false, e.stream));
+  e.kernel_launches++;
+  return QCS_CUDA_OK;
+}
+
+// ------------------------------------------------------------------ executing gates
+static PhysGate to_phys(const Engine &e, const HostGate &g) {
+  PhysGate p;
+  p.c = classify_gate(g.m, g.control >= 0, e.opt.sem);
+  p.tpos = e.perm[g.target];
+  p.cpos = g.control >= 0 ? e.perm[g.control] : -1;
+  return p;
+}
+
+static bool is_pairing_kind(uint8_t k) {
+  return k == GK_PAIR_GENERIC || k == GK_PAIR_REAL || k == GK_PAIR_HSYM || k == GK_PAIR_SWAP;
+}
+
+// SURVEY.md section 8(d) byte accounting for one gate executed on its own.
+static double gate_bytes(const Engine &e, const PhysGate &g) {
+  const double amps = (double)e.local_size;
+  if (g.c.kind == GK_NOP) return 0.0;
+  double frac = 1.0;
+  if (g.cpos >= 0) frac *= 0.5;
+  if (g.c.kind == GK_DIAG) {
+    int touched = ((g.c.flags & GF_D0_IDENT) ? 0 : 1) + ((g.c.flags & GF_D1_IDENT) ? 0 : 1);
+    frac *= 0.5 * touched;
+  } else if (g.c.flags & GF_ROW0_ONLY) {
+    frac *= 0.75;  // read both members, write one
+  }
+  return 32.0 * amps * frac;
+}
+
+// Runs a list of physical gates whose pairing targets are all local.
+static int run_local(Engine &e, const std::vector<PhysGate> &gates, bool record_plan) {
+  if (gates.empty()) return QCS_CUDA_OK;
+  const bool fused = e.opt.fusion && e.nl >= QCS_TILE_BITS;
+  if (fused) {
+    PlannerConfig cfg;
+    cfg.n_local = e.nl;
+    cfg.rank_bits = e.n - e.nl;
+    cfg.shard_base = e.shard_base;
+    cfg.sem = e.opt.sem;
+    cfg.pass_flops_budget = e.opt.pass_flops;
+    cfg.direct_io = true;
+    cfg.reg_bits = (e.opt.tile_kernel == 2) ? 3 : 4;
+    std::vector<PassPlan> plan = plan_passes(gates, cfg);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e.timing && !e.opt.dryrun && !plan.empty()) {
+      ev0 = get_event(e);
+      ev1 = get_event(e);
+      cudaEventRecord(ev0, e.stream);
+    }
+    for (const PassPlan &p : plan) {
+      if (!e.opt.dryrun) {
+        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel));
+      }
+      e.passes++;
+      e.kernel_launches++;
+      e.segments += p.params.n_segments;
+      e.gates_executed += p.params.n_gates;
+      const double bytes = 32.0 * (double)e.local_size;
+      e.algorithmic_bytes += bytes;
+      e.pass_bytes += bytes;
+    }
+    if (ev0) {
+      cudaEventRecord(ev1, e.stream);
+      e.pending_pass_events.emplace_back(ev0, ev1);
+      if (e.pending_pass_events.size() > 512) fold_events(e);
+    }
+    if (record_plan) {
+      for (auto &p : plan) e.last_plan.push_back(p);
+    }
+  } else {
+    for (const PhysGate &g : gates) {
+      if (g.c.kind == GK_NOP) continue;
+      DGate dg;
+      std::memset(&dg, 0, sizeof(dg));
+      std::memcpy(dg.m, g.c.m, sizeof(dg.m));
+      dg.kind = g.c.kind;
+      dg.flags = g.c.flags;
+      dg.tpos = (int8_t)g.tpos;
+      dg.cpos = (int8_t)g.cpos;
+      dg.op = QCS_OP_NONE;
+      dg.ctest = dg.tsel = 0xFF;
+      if (!e.opt.dryrun) CK(launch_simple_gate(e.live, dg, e.nl, e.shard_base, e.stream));
+      e.kernel_launches++;
+      e.gates_executed++;
+      e.algorithmic_bytes += gate_bytes(e, g);
+    }
+  }
+  return QCS_CUDA_OK;
+}
+
+// Picks the local position to trade for global position `gpos`: the local
+// qubit whose next use as a pairing target lies farthest ahead in the queue.
+static int pick_victim(const Engine &e, const std::vector<HostGate> &q, size_t from) {
+  std::vector<long> next_use(e.nl, (long)q.size() + 1);
+  for (size_t i = q.size(); i-- > from;) {
+    Classified c = classify_gate(q[i].m, q[i].control >= 0, e.opt.sem);
+    if (!is_pairing_kind(c.kind)) continue;
+    int pos = e.perm[q[i].target];
+    if (pos < e.nl) next_use[pos] = (long)i;
+  }
+  int best = e.nl - 1;
+  long best_use = -1;
+  // Prefer high positions (long contiguous rows stay intact) among equally idle ones;
+  // never trade positions 0..4 (lane bits of every tile).
+  for (int pos = e.nl - 1; pos >= QCS_LANE_BITS && pos >= 0; pos--) {
+    if (next_use[pos] > best_use) {
+      best_use = next_use[pos];
+      best = pos;
+    }
+  }
+  return best;
+}
+
+static int swap_positions(Engine &e, int lpos, int gpos) {
+  if (!e.opt.dryrun) RC(dist_swap_positions(e, lpos, gpos));
+  const int ql = e.inv_perm[lpos], qg = e.inv_perm[gpos];
+  e.perm[ql] = gpos;
+  e.perm[qg] = lpos;
+  e.inv_perm[lpos] = qg;
+  e.inv_perm[gpos] = ql;
+  e.remaps++;
+  e.exchange_bytes += 8.0 * (double)e.local_size;
+  return QCS_CUDA_OK;
+}
+
+// Executes queue[begin, end): cuts at pairing gates whose target is global,
+// remaps, continues.
+static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, size_t end) {
+  std::vector<PhysGate> batch;
+  for (size_t i = begin; i < end; i++) {
+    PhysGate p = to_phys(e, q[i]);
+    if (is_pairing_kind(p.c.kind) && p.tpos >= e.nl) {
+      RC(run_local(e, batch, true));
+      batch.clear();
+      const int victim = pick_victim(e, q, i);
+      RC(swap_positions(e, victim, p.tpos));
+      p = to_phys(e, q[i]);
+    }
+    batch.push_back(p);
+  }
+  RC(run_local(e, batch, true));
+  return QCS_CUDA_OK;
+}
+
+static int flush(Engine &e) {
+  if (e.queue.empty()) return QCS_CUDA_OK;
+  std::vector<HostGate> q;
+  q.swap(e.queue);
+  e.last_plan.clear();
+  if (e.opt.sem == SEM_REFERENCE) {
+    // Scratch-observability rule: after any gate the
+    // reference's scratch buffer holds the complete pre-gate state.  Execute
+    // all but the last gate fused in place, snapshot, then the last gate.
+    RC(run_range(e, q, 0, q.size() - 1));
+    RC(ensure_scratch(e));
+    if (!e.opt.dryrun) {
+      CK(cudaMemcpyAsync(e.scratch, e.live, e.local_size * sizeof(double2),
+                         cudaMemcpyDeviceToDevice, e.stream));
+    }
+    RC(run_range(e, q, q.size() - 1, q.size()));
+  } else {
+    RC(run_range(e, q, 0, q.size()));
+  }
+  return QCS_CUDA_OK;
+}
+
+// Restores the identity qubit layout (needed by every order-dependent read).
+static int canonicalize(Engine &e) {
+  for (int g = e.nl; g < e.n; g++) {
+    while (e.inv_perm[g] != g) {
+      // logical qubit g currently sits at local position perm[g] (or another global one)
+      const int where = e.perm[g];
+      if (where < e.nl) {
+        RC(swap_positions(e, where, g));
+      } else {
+        // two global positions hold each other's qubits: route through a local position
+        RC(swap_positions(e, e.nl - 1, where));
+      }
+    }
+  }
+  // local-local permutations never arise: swaps only trade a local for a global position,
+  // and restoring every global position restores the locals too.
+  for (int q = 0; q < e.n; q++)
+    if (e.perm[q] != q) return set_error(QCS_CUDA_ERR_CUDA, "internal: layout not canonical");
+  return QCS_CUDA_OK;
+}
+
+static int require_data(const Engine &e) {
+  if (e.opt.dryrun) return set_error(QCS_CUDA_ERR_DRYRUN, "plan-only engine holds no amplitudes");
+  return QCS_CUDA_OK;
+}
+
+// Exact left-to-right sum of |a|^2 over the whole logical state (all ranks),
+// optionally masked to indices with bit `pos` clear.  Leaves chunk_exact on
+// every rank; *total is the same on every rank.
+static int exact_total(Engine &e, int pos, double *total) {
+  DistContext &d = dist();
+  double *res = e.ws.result;
+  int mask_local = (pos >= 0 && pos < e.nl) ? pos : -1;
+  // a masked GLOBAL position: whole shards either count or not
+  const bool shard_counts = !(pos >= e.nl && ((e.shard_base >> pos) & 1ull));
+  if (!d.active) {
+    CK(launch_chunk_sums(e.live, e.local_size, mask_local, e.ws, e.stream));
+    CK(launch_chunk_deltas(e.live, e.local_size, mask_local, res + RES_ZERO, e.ws, e.stream));
+    CK(launch_chunk_resolve(e.live, e.local_size, mask_local, res + RES_ZERO, e.ws, e.stream));
+    e.kernel_launches += 5;
+    CK(cudaMemcpyAsync(total, res + RES_EXACT_TOTAL, sizeof(double), cudaMemcpyDeviceToHost,
+                       e.stream));
+    CK(cudaStreamSynchronize(e.stream));
+    e.algorithmic_bytes += 2 * 16.0 * (double)e.local_size * (mask_local >= 0 ? 0.5 : 1.0);
+    return QCS_CUDA_OK;
+  }
+  // Multi-rank: approximate offsets first (parallel), then the exact walk chained rank by rank.
+  std::vector<double> approx_tot(d.world, 0.0);
+  double mine = 0.0;
+  if (shard_counts) {
+    CK(launch_chunk_sums(e.live, e.local_size, mask_local, e.ws, e.stream));
+    e.kernel_launches += 2;
+    if (e.local_size >= (uint64_t)SEQ_CHUNK) {
+      CK(cudaMemcpyAsync(&mine, res + RES_APPROX_TOTAL, sizeof(double), cudaMemcpyDeviceToHost,
+                         e.stream));
+      CK(cudaStreamSynchronize(e.stream));
+    }
+  }
+  RC(dist_allgather_host(&mine, approx_tot.data(), sizeof(double)));
+  double approx_start = 0.0;
+  for (int r = 0; r < d.rank; r++) approx_start += approx_tot[r];
+  CK(cudaMemcpyAsync(res + RES_START, &approx_start, sizeof(double), cudaMemcpyHostToDevice,
+                     e.stream));
+  if (shard_counts) {
+    CK(launch_chunk_deltas(e.live, e.local_size, mask_local, res + RES_START, e.ws, e.stream));
+    e.kernel_launches += 2;
+  }
+  // exact chain: rank r starts from the exact running sum after rank r-1
+  std::vector<double> exact_after(d.world, 0.0);
+  double running = 0.0;
+  for (int r = 0; r < d.world; r++) {
+    if (r == d.rank) {
+      if (shard_counts) {
+        CK(cudaMemcpyAsync(res + RES_START + 1, &running, sizeof(double), cudaMemcpyHostToDevice,
+                           e.stream));
+        CK(launch_chunk_resolve(e.live, e.local_size, mask_local, res + RES_START + 1, e.ws,
+                                e.stream));
+        e.kernel_launches++;
+        CK(cudaMemcpyAsync(&mine, res + RES_EXACT_TOTAL, sizeof(double), cudaMemcpyDeviceToHost,
+                           e.stream));
+        CK(cudaStreamSynchronize(e.stream));
+      } else {
+        mine = running;
+      }
+    }
+    double tmp = (r == d.rank) ? mine : 0.0;
+    std::vector<double> all(d.world, 0.0);
+    RC(dist_allgather_host(&tmp, all.data(), sizeof(double)));
+    running = all[r];
+    exact_after[r] = running;
+  }
+  *total = running;
+  return QCS_CUDA_OK;
+}
+
+static int normalize_now(Engine &e) {
+  double total = 0.0;
+  RC(exact_total(e, -1, &total));
+  // q_state_normalize (reference src/q_utils.c:111-117)
+  if (total > 1e-12 && total != 1.0) {
+    const double inv = 1.0 / std::sqrt(total);
+    CK(launch_scale(e.live, e.local_size, inv, e.stream));
+    e.kernel_launches++;
+    e.algorithmic_bytes += 32.0 * (double)e.local_size;
+  }
+  return QCS_CUDA_OK;
+}
+
+}  // namespace qcs
+
+// ====================================================================== ABI
+using namespace qcs;
+
+extern "C" {
+
+const char *qcs_cuda_last_error(void) { return g_error; }
+
+int qcs_cuda_set_default(const char *key, const char *value) {
+  if (!key) return set_error(QCS_CUDA_ERR_INVALID, "null key");
+  if (!value) defaults().erase(key);
+  else defaults()[key] = value;
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
+  if (!out) return set_error(QCS_CUDA_ERR_INVALID, "null out pointer");
+  *out = nullptr;
+  if (n_qubits <= 0)  // reference: "Number of qubits must be positive" (src/q_state.c:38-41)
+    return set_error(QCS_CUDA_ERR_INVALID, "Number of qubits must be positive.");
+  DistContext &d = dist();
+  const int rank_bits = d.active ? d.rank_bits : 0;
+  if (n_qubits > 40 || n_qubits - rank_bits < 1)
+    return set_error(QCS_CUDA_ERR_INVALID, "unsupported qubit count %d for %d rank(s)", n_qubits,
+                     d.active ? d.world : 1);
+  qcs_cuda_engine *e = new qcs_cuda_engine();
+  int rc = load_options(e->opt);
+  if (rc != QCS_CUDA_OK) {
+    delete e;
+    return rc;
+  }
+  e->n = n_qubits;
+  e->nl = n_qubits - rank_bits;
+  e->local_size = 1ull << e->nl;
+  e->shard_base = d.active ? ((uint64_t)d.rank << e->nl) : 0ull;
+  for (int q = 0; q < 64; q++) e->perm[q] = e->inv_perm[q] = q;
+  if (e->opt.dryrun) {
+    *out = e;
+    return QCS_CUDA_OK;
+  }
+  auto fail = [&](int code) {
+    qcs_cuda_state_destroy(e);
+    return code;
+  };
+  std::string dev = option_value("device");
+  if (d.active) {
+    rc = check_cuda(cudaSetDevice(d.device), "cudaSetDevice");
+  } else if (!dev.empty()) {
+    rc = check_cuda(cudaSetDevice(std::atoi(dev.c_str())), "cudaSetDevice");
+  } else {
+    int cur = 0;
+    rc = check_cuda(cudaGetDevice(&cur), "cudaGetDevice (no CUDA device: QCS_GPU_CUDA has no CPU fallback)");
+  }
+  if (rc) return fail(rc);
+  if ((rc = check_cuda(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate")))
+    return fail(rc);
+  if ((rc = check_cuda(cudaMalloc(&e->live, e->local_size * sizeof(double2)), "cudaMalloc(state)")))
+    return fail(rc);
+  ReduceWorkspace &ws = e->ws;
+  const size_t n_chunks = e->local_size >= SEQ_CHUNK ? e->local_size / SEQ_CHUNK : 1;
+  ws.n_chunks_cap = n_chunks;
+  if ((rc = check_cuda(cudaMalloc(&ws.partials, 4 * REDUCE_MAX_BLOCKS * sizeof(double)), "cudaMalloc")) ||
+      (rc = check_cuda(cudaMalloc(&ws.ipartials, REDUCE_MAX_BLOCKS * sizeof(long long)), "cudaMalloc")) ||
+      (rc = check_cuda(cudaMalloc(&ws.result, RES_COUNT * sizeof(double)), "cudaMalloc")) ||
+      (rc = check_cuda(cudaMalloc(&ws.iresult, 4 * sizeof(long long)), "cudaMalloc")) ||
+      (rc = check_cuda(cudaMalloc(&ws.chunk_sum, n_chunks * sizeof(double)), "cudaMalloc")) ||
+      (rc = check_cuda(cudaMalloc(&ws.chunk_approx, (n_chunks + 1) * sizeof(double)), "cudaMalloc")) ||
+      (rc = check_cuda(cudaMalloc(&ws.chunk_delta, n_chunks * sizeof(double)), "cudaMalloc")) ||
+      (rc = check_cuda(cudaMalloc(&ws.chunk_flag, n_chunks), "cudaMalloc")) ||
+      (rc = check_cuda(cudaMalloc(&ws.chunk_exact, (n_chunks + 1) * sizeof(double)), "cudaMalloc")))
+    return fail(rc);
+  if ((rc = check_cuda(cudaMemsetAsync(ws.result, 0, RES_COUNT * sizeof(double), e->stream), "cudaMemset")))
+    return fail(rc);
+  // zero everything, amplitude 0 := 1 (reference src/q_state.c:93-99)
+  const bool owns_zero = !d.active || d.rank == 0;
+  if ((rc = check_cuda(launch_init_state(e->live, e->local_size, owns_zero, e->stream), "init_state")))
+    return fail(rc);
+  e->kernel_launches++;
+  if ((rc = check_cuda(cudaStreamSynchronize(e->stream), "init sync"))) return fail(rc);
+  *out = e;
+  return QCS_CUDA_OK;
+}
+
+void qcs_cuda_state_destroy(qcs_cuda_engine *e) {
+  if (!e) return;
+  if (e->opt.dryrun) {
+    delete e;
+    return;
+  }
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (auto &pr : e->pending_pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (auto &pr : e->pending_xchg_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (auto ev : e->event_pool) cudaEventDestroy(ev);
+  cudaFree(e->live);
+  cudaFree(e->scratch);
+  cudaFree(e->staging);
+  cudaFree(e->ws.partials);
+  cudaFree(e->ws.ipartials);
+  cudaFree(e->ws.result);
+  cudaFree(e->ws.iresult);
+  cudaFree(e->ws.chunk_sum);
+  cudaFree(e->ws.chunk_approx);
+  cudaFree(e->ws.chunk_delta);
+  cudaFree(e->ws.chunk_flag);
+  cudaFree(e->ws.chunk_exact);
+  cudaFree(e->u_dev);
+  cudaFree(e->idx_dev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int qcs_cuda_num_qubits(const qcs_cuda_engine *e) { return e ? e->n : 0; }
+
+int qcs_cuda_apply_1q(qcs_cuda_engine *e, const double m[8], int target) {
+  if (!e || !m) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  if (target < 0 || target >= e->n)  // reference src/q_gates.c:32-36
+    return set_error(QCS_CUDA_ERR_INVALID, "Invalid arguments for 1-qubit gate application.");
+  HostGate g;
+  std::memcpy(g.m, m, sizeof(g.m));
+  g.target = target;
+  g.control = -1;
+  e->queue.push_back(g);
+  e->gates_submitted++;
+  if (e->queue.size() >= 4096) return flush(*e);
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_apply_c1q(qcs_cuda_engine *e, const double m[8], int control, int target) {
+  if (!e || !m) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  if (control < 0 || target < 0 || control >= e->n || target >= e->n || control == target)
+    return set_error(QCS_CUDA_ERR_INVALID, "Invalid arguments for 2-qubit gate application.");  // :165-170
+  HostGate g;
+  std::memcpy(g.m, m, sizeof(g.m));
+  g.target = target;
+  g.control = control;
+  e->queue.push_back(g);
+  e->gates_submitted++;
+  if (e->queue.size() >= 4096) return flush(*e);
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_flush(qcs_cuda_engine *e) {
+  if (!e) return set_error(QCS_CUDA_ERR_INVALID, "null engine");
+  RC(flush(*e));
+  if (!e->opt.dryrun) CK(cudaStreamSynchronize(e->stream));
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_phase_flip(qcs_cuda_engine *e, long index) {
+  if (!e) return set_error(QCS_CUDA_ERR_INVALID, "null engine");
+  if (index < 0 || (uint64_t)index >= (1ull << e->n))  // reference src/q_gates.c:306-309
+    return set_error(QCS_CUDA_ERR_INVALID, "Invalid state or index for phase flip.");
+  RC(flush(*e));
+  RC(canonicalize(*e));
+  if (e->opt.dryrun) return QCS_CUDA_OK;
+  const bool mine = ((uint64_t)index >> e->nl) == (e->shard_base >> e->nl);
+  const uint64_t local = (uint64_t)index & (e->local_size - 1);
+  if (e->opt.sem == SEM_REFERENCE) {
+    // swap buffers, then live[idx] = -scratch[idx] (reference src/q_gates.c:311-316)
+    RC(ensure_scratch(*e));
+    std::swap(e->live, e->scratch);
+    if (mine) {
+      CK(launch_negate_one(e->live, e->scratch, local, e->stream));
+      e->kernel_launches++;
+    }
+  } else if (mine) {
+    CK(launch_negate_one(e->live, e->live, local, e->stream));
+    e->kernel_launches++;
+  }
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_diffusion(qcs_cuda_engine *e) {
+  if (!e) return set_error(QCS_CUDA_ERR_INVALID, "null engine");
+  RC(flush(*e));
+  if (e->opt.dryrun) return QCS_CUDA_OK;
+  CK(launch_complex_sum(e->live, e->local_size, e->ws, e->stream));
+  if (dist().active) RC(dist_allreduce_sum(*e, e->ws.result + RES_SUM_RE, 2));
+  CK(launch_diffusion_mean(e->ws, e->opt.sem == SEM_CORRECTED, (double)(1ull << e->n), e->stream));
+  if (e->opt.sem == SEM_REFERENCE) {
+    // new values go to the other buffer, then the buffers trade roles (:348-355)
+    RC(ensure_scratch(*e));
+    CK(launch_diffusion_write(e->live, e->scratch, e->local_size, e->ws, e->stream));
+    std::swap(e->live, e->scratch);
+  } else {
+    CK(launch_diffusion_write(e->live, e->live, e->local_size, e->ws, e->stream));
+  }
+  e->kernel_launches += 4;
+  e->algorithmic_bytes += 48.0 * (double)e->local_size;
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_normalize(qcs_cuda_engine *e) {
+  if (!e) return set_error(QCS_CUDA_ERR_INVALID, "null engine");
+  RC(flush(*e));
+  RC(require_data(*e));
+  RC(canonicalize(*e));
+  return normalize_now(*e);
+}
+
+int qcs_cuda_prob0(qcs_cuda_engine *e, int qubit, double *p0) {
+  if (!e || !p0) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  if (qubit < 0 || qubit >= e->n) return set_error(QCS_CUDA_ERR_INVALID, "qubit out of range");
+  RC(flush(*e));
+  RC(require_data(*e));
+  RC(canonicalize(*e));
+  return exact_total(*e, qubit, p0);
+}
+
+int qcs_cuda_collapse(qcs_cuda_engine *e, int qubit, int outcome) {
+  if (!e) return set_error(QCS_CUDA_ERR_INVALID, "null engine");
+  if (qubit < 0 || qubit >= e->n || (outcome != 0 && outcome != 1))
+    return set_error(QCS_CUDA_ERR_INVALID, "bad collapse arguments");
+  RC(flush(*e));
+  RC(require_data(*e));
+  RC(canonicalize(*e));
+  if (qubit < e->nl) {
+    CK(launch_zero_half(e->live, e->local_size, qubit, outcome, e->stream));
+    e->algorithmic_bytes += 8.0 * (double)e->local_size;
+  } else if ((int)((e->shard_base >> qubit) & 1ull) != outcome) {
+    CK(launch_init_state(e->live, e->local_size, false, e->stream));
+    e->algorithmic_bytes += 16.0 * (double)e->local_size;
+  }
+  e->kernel_launches++;
+  return normalize_now(*e);
+}
+
+int qcs_cuda_read_amplitudes(qcs_cuda_engine *e, int which, long first, long count, double *out) {
+  if (!e || !out) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  RC(flush(*e));
+  RC(require_data(*e));
+  RC(canonicalize(*e));
+  const uint64_t base = e->shard_base;
+  if (first < 0 || count < 0 || (uint64_t)first < base ||
+      (uint64_t)first + (uint64_t)count > base + e->local_size)
+    return set_error(QCS_CUDA_ERR_INVALID, "amplitude range [%ld, %ld) is not inside this rank's shard", first, first + count);
+  const double2 *src = which ? e->scratch : e->live;
+  if (which && !src) {  // never touched: still the zeros of q_state_init
+    std::memset(out, 0, (size_t)count * 16);
+    return QCS_CUDA_OK;
+  }
+  CK(cudaMemcpyAsync(out, src + ((uint64_t)first - base), (size_t)count * sizeof(double2),
+                     cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_write_amplitudes(qcs_cuda_engine *e, int which, long first, long count, const double *in) {
+  if (!e || !in) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  RC(flush(*e));
+  RC(require_data(*e));
+  RC(canonicalize(*e));
+  const uint64_t base = e->shard_base;
+  if (first < 0 || count < 0 || (uint64_t)first < base ||
+      (uint64_t)first + (uint64_t)count > base + e->local_size)
+    return set_error(QCS_CUDA_ERR_INVALID, "amplitude range is not inside this rank's shard");
+  if (which) RC(ensure_scratch(*e));
+  double2 *dst = which ? e->scratch : e->live;
+  CK(cudaMemcpyAsync(dst + ((uint64_t)first - base), in, (size_t)count * sizeof(double2),
+                     cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_get_amplitude(qcs_cuda_engine *e, long index, double out[2]) {
+  if (!e || !out) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  if (index < 0 || (uint64_t)index >= (1ull << e->n))
+    return set_error(QCS_CUDA_ERR_INVALID, "state index out of range");
+  RC(flush(*e));
+  RC(require_data(*e));
+  RC(canonicalize(*e));
+  double2 v = make_double2(0.0, 0.0);
+  const bool mine = ((uint64_t)index >> e->nl) == (e->shard_base >> e->nl);
+  if (mine) {
+    CK(cudaMemcpyAsync(&v, e->live + ((uint64_t)index & (e->local_size - 1)), sizeof(v),
+                       cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  if (dist().active) {
+    std::vector<double2> all(dist().world);
+    RC(dist_allgather_host(&v, all.data(), sizeof(v)));
+    v = all[(uint64_t)index >> e->nl];
+  }
+  out[0] = v.x;
+  out[1] = v.y;
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_probability(qcs_cuda_engine *e, long index, double *p) {
+  if (!e || !p) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  if (index < 0 || (uint64_t)index >= (1ull << e->n)) {  // reference src/qcs.c:392-393
+    *p = 0.0;
+    return QCS_CUDA_OK;
+  }
+  double a[2];
+  RC(qcs_cuda_get_amplitude(e, index, a));
+  *p = (a[0] * a[0]) + (a[1] * a[1]);  // c_norm_sq; host FMA contraction is off (-ffp-contract=off)
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_argmax(qcs_cuda_engine *e, long *index) {
+  if (!e || !index) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  RC(flush(*e));
+  RC(require_data(*e));
+  RC(canonicalize(*e));
+  CK(launch_argmax(e->live, e->local_size, e->ws, e->stream));
+  e->kernel_launches += 2;
+  e->algorithmic_bytes += 16.0 * (double)e->local_size;
+  struct { double p; long long idx; } mine{0.0, 0};
+  CK(cudaMemcpyAsync(&mine.p, e->ws.result, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(&mine.idx, e->ws.iresult, sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  mine.idx += (long long)e->shard_base;
+  if (dist().active) {
+    std::vector<decltype(mine)> all(dist().world);
+    RC(dist_allgather_host(&mine, all.data(), sizeof(mine)));
+    double best_p = 0.0;
+    long long best_i = 0;
+    for (auto &c : all)  // ascending rank == ascending index: strict > keeps the first maximum
+      if (c.p > best_p) { best_p = c.p; best_i = c.idx; }
+    mine.idx = best_i;
+  }
+  *index = (long)mine.idx;
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_sample(qcs_cuda_engine *e, const double *u, int shots, long *indices) {
+  if (!e || !u || !indices) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  if (shots <= 0) return QCS_CUDA_OK;
+  RC(flush(*e));
+  RC(require_data(*e));
+  RC(canonicalize(*e));
+  double total = 0.0;
+  RC(exact_total(*e, -1, &total));
+  if (shots > e->shots_cap) {
+    cudaFree(e->u_dev);
+    cudaFree(e->idx_dev);
+    e->u_dev = nullptr;
+    e->idx_dev = nullptr;
+    e->shots_cap = 0;
+    CK(cudaMalloc(&e->u_dev, (size_t)shots * sizeof(double)));
+    CK(cudaMalloc(&e->idx_dev, (size_t)shots * sizeof(long long)));
+    e->shots_cap = shots;
+  }
+  CK(cudaMemcpyAsync(e->u_dev, u, (size_t)shots * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  CK(launch_sample(e->live, e->local_size, e->ws, e->u_dev, shots, e->idx_dev,
+                   (long long)e->shard_base, e->stream));
+  e->kernel_launches++;
+  static_assert(sizeof(long) == sizeof(long long), "LP64 expected");
+  // multi-rank: exactly one rank found each surviving shot, everyone else wrote -1
+  RC(dist_allreduce_max_i64(*e, e->idx_dev, (size_t)shots));
+  CK(cudaMemcpyAsync(indices, e->idx_dev, (size_t)shots * sizeof(long long), cudaMemcpyDeviceToHost,
+                     e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_set_timing(qcs_cuda_engine *e, int enabled) {
+  if (!e) return set_error(QCS_CUDA_ERR_INVALID, "null engine");
+  e->timing = enabled != 0;
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out) {
+  if (!e || !out) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  fold_events(*e);
+  out->gates_submitted = e->gates_submitted;
+  out->gates_executed = e->gates_executed;
+  out->passes = e->passes;
+  out->kernel_launches = e->kernel_launches;
+  out->segments = e->segments;
+  out->remaps = e->remaps;
+  out->algorithmic_bytes = e->algorithmic_bytes;
+  out->pass_bytes = e->pass_bytes;
+  out->pass_ms = e->pass_ms;
+  out->exchange_bytes = e->exchange_bytes;
+  out->exchange_ms = e->exchange_ms;
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_reset_stats(qcs_cuda_engine *e) {
+  if (!e) return set_error(QCS_CUDA_ERR_INVALID, "null engine");
+  fold_events(*e);
+  e->gates_submitted = e->gates_executed = e->passes = e->kernel_launches = e->segments = e->remaps = 0;
+  e->algorithmic_bytes = e->pass_bytes = e->pass_ms = e->exchange_bytes = e->exchange_ms = 0;
+  return QCS_CUDA_OK;
+}
+
+long qcs_cuda_describe_last_plan(qcs_cuda_engine *e, char *buf, long cap) {
+  if (!e) return 0;
+  std::string s = describe_plan(e->last_plan);
+  if (buf && cap > 0) {
+    long n = (long)s.size() < cap - 1 ? (long)s.size() : cap - 1;
+    std::memcpy(buf, s.data(), (size_t)n);
+    buf[n] = 0;
+  }
+  return (long)s.size() + 1;
+}
+
+}  // extern "C"

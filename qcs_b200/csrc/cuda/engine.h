@@ -1,0 +1,84 @@
+// engine.h -- internal definition of qcs_cuda_engine (the handle behind the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "kernels.h"
+#include "planner.h"
+
+struct qcs_cuda_stats;
+
+namespace qcs {
+
+struct Options {
+  Semantics sem = SEM_REFERENCE;
+  bool fusion = true;
+  bool dryrun = false;
+  double pass_flops = 96.0;
+  int exchange = 0;  // 0: NCCL send/recv, 1: peer-memory swap kernel
+  int tile_kernel = 2;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8)
+};
+
+struct DistContext {
+  bool active = false;
+  int rank = 0;
+  int world = 1;
+  int rank_bits = 0;
+  int device = 0;
+  void *comm = nullptr;  // ncclComm_t
+};
+
+DistContext &dist();
+
+struct Engine {
+  int n = 0;        // logical qubits
+  int nl = 0;       // local (per-shard) qubits
+  uint64_t local_size = 0;
+  uint64_t shard_base = 0;  // rank << nl
+  Options opt;
+
+  double2 *live = nullptr;     // reference: state->vector
+  double2 *scratch = nullptr;  // reference: state->scratch_vector (lazily allocated)
+  double2 *staging = nullptr;  // half-shard exchange buffer (multi-GPU)
+  cudaStream_t stream = nullptr;
+  ReduceWorkspace ws{};
+  double *u_dev = nullptr;
+  long long *idx_dev = nullptr;
+  int shots_cap = 0;
+
+  // logical qubit -> physical position and back
+  int perm[64];
+  int inv_perm[64];
+
+  std::vector<HostGate> queue;
+  std::vector<PassPlan> last_plan;
+
+  // statistics
+  long long gates_submitted = 0, gates_executed = 0, passes = 0, kernel_launches = 0,
+            segments = 0, remaps = 0;
+  double algorithmic_bytes = 0, pass_bytes = 0, pass_ms = 0, exchange_bytes = 0, exchange_ms = 0;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_pass_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_xchg_events;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+// engine.cu
+int set_error(int code, const char *fmt, ...);
+int check_cuda(cudaError_t e, const char *what);
+
+// dist.cu
+// Swaps physical positions `lpos` (local) and `gpos` (global) of the shard
+// layout with the partner rank (half of the shard crosses NVLink).
+int dist_swap_positions(Engine &e, int lpos, int gpos);
+int dist_allreduce_sum(Engine &e, double *dev_values, int count);
+int dist_allreduce_max_i64(Engine &e, long long *dev_values, size_t count);
+int dist_allgather_host(const void *mine, void *all, size_t bytes_each);
+int dist_barrier(Engine &e);
+
+}  // namespace qcs
+
+struct qcs_cuda_engine : public qcs::Engine {};

@@ -1,0 +1,74 @@
+// kernels.h -- launchers implemented in the .cu files (all asynchronous on `stream`).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.h"
+
+namespace qcs {
+
+// kernels_fused.cu ----------------------------------------------------------
+// variant 0: one CTA per tile, plain 128-bit global loads/stores
+// variant 1: persistent CTAs, tiles staged through shared memory by TMA bulk copies
+cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
+                              cudaStream_t stream, int variant);
+
+// kernels_simple.cu: one launch per gate (fusion off, shards below one tile) ---
+cudaError_t launch_simple_gate(double2 *state, const DGate &g, int n_local,
+                               uint64_t shard_base, cudaStream_t stream);
+
+// kernels_reduce.cu -----------------------------------------------------------
+struct ReduceWorkspace {
+  double *partials;        // device, >= 4 * REDUCE_MAX_BLOCKS doubles
+  long long *ipartials;    // device, >= REDUCE_MAX_BLOCKS
+  double *result;          // device, RES_COUNT doubles
+  long long *iresult;      // device, 2 long longs
+  // exact sequential-prefix machinery (chunked)
+  double *chunk_sum;       // device, n_chunks
+  double *chunk_approx;    // device, n_chunks + 1
+  double *chunk_delta;     // device, n_chunks
+  unsigned char *chunk_flag;  // device, n_chunks
+  double *chunk_exact;     // device, n_chunks + 1
+  size_t n_chunks_cap;
+};
+enum { REDUCE_MAX_BLOCKS = 4096, SEQ_CHUNK = 1024 };
+
+cudaError_t launch_init_state(double2 *state, uint64_t n_amps, bool set_one, cudaStream_t s);
+cudaError_t launch_complex_sum(const double2 *state, uint64_t n_amps, ReduceWorkspace &ws,
+                               cudaStream_t s);  // result[0..1] = sum re, sum im
+// result[0..1] (raw sum) -> result[2..3] = 2*mean, per semantics (device-side, no host sync)
+cudaError_t launch_diffusion_mean(ReduceWorkspace &ws, bool corrected, double n_total,
+                                  cudaStream_t s);
+// dst[i] = 2*mean - src[i]   (dst may alias src)
+cudaError_t launch_diffusion_write(const double2 *src, double2 *dst, uint64_t n_amps,
+                                   const ReduceWorkspace &ws, cudaStream_t s);
+cudaError_t launch_scale(double2 *state, uint64_t n_amps, double factor, cudaStream_t s);
+cudaError_t launch_zero_half(double2 *state, uint64_t n_amps, int pos, int keep_bit,
+                             cudaStream_t s);
+cudaError_t launch_negate_one(double2 *dst, const double2 *src, uint64_t index, cudaStream_t s);
+cudaError_t launch_argmax(const double2 *state, uint64_t n_amps, ReduceWorkspace &ws,
+                          cudaStream_t s);  // result[0] = max prob, iresult[0] = first index
+
+// Exact replay of the reference's left-to-right rounded accumulation of
+// |a_i|^2 (optionally only over indices with bit `mask_pos` clear; -1 = all).
+// Three stream-ordered phases so that ranks can chain their shards:
+//   launch_chunk_sums    K1: tree sum per 1024-term chunk; result[RES_APPROX_TOTAL] = shard total
+//   launch_chunk_deltas  K2+K3: approximate prefix from *approx_start_dev, per-chunk increments
+//   launch_chunk_resolve K4: exact walk from *exact_start_dev; chunk_exact[k] = running sum
+//                        before chunk k (k = 0..n_chunks), result[RES_EXACT_TOTAL] = after the shard
+enum { RES_SUM_RE = 0, RES_SUM_IM = 1, RES_TWO_MEAN_RE = 2, RES_TWO_MEAN_IM = 3,
+       RES_APPROX_TOTAL = 4, RES_EXACT_TOTAL = 5, RES_ZERO = 6, RES_START = 7, RES_COUNT = 16 };
+cudaError_t launch_chunk_sums(const double2 *state, uint64_t n_amps, int mask_pos,
+                              ReduceWorkspace &ws, cudaStream_t s);
+cudaError_t launch_chunk_deltas(const double2 *state, uint64_t n_amps, int mask_pos,
+                                const double *approx_start_dev, ReduceWorkspace &ws,
+                                cudaStream_t s);
+cudaError_t launch_chunk_resolve(const double2 *state, uint64_t n_amps, int mask_pos,
+                                 const double *exact_start_dev, ReduceWorkspace &ws,
+                                 cudaStream_t s);
+// Per shot: smallest i with u < running sum; -1 if none.  Needs launch_chunk_resolve first.
+cudaError_t launch_sample(const double2 *state, uint64_t n_amps, const ReduceWorkspace &ws,
+                          const double *u_dev, int shots, long long *idx_dev,
+                          long long index_offset, cudaStream_t s);
+
+}  // namespace qcs

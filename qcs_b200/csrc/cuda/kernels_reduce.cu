@@ -1,0 +1,561 @@
+// kernels_reduce.cu -- reductions, collapse, diffusion and the exact
+// sequential-prefix machinery behind measurement and sampling.
+//
+// Reference loops replaced here:
+//   prob_0 masked sum + collapse ....... reference src/qcs.c:253-281
+//   q_state_normalize .................. reference src/q_utils.c:103-117
+//   q_apply_diffusion .................. reference src/q_gates.c:334-355
+//   q_apply_phase_flip ................. reference src/q_gates.c:311-316
+//   qc_find_most_likely_state .......... reference src/qcs.c:464-478
+//   qc_run_shots CDF scan .............. reference src/qcs.c:589-605
+//
+// Exactness.  The reference accumulates |a_i|^2 left to right in one double,
+// and its decisions (`u <= prob_0`, `u < cumulative`, `total != 1.0`) depend
+// on that rounded running sum.  A parallel tree sum differs in the last bits,
+// so instead the running sum is REPLAYED exactly, in parallel:
+//   while the running sum S stays inside one binade [2^e, 2^(e+1)) every
+//   addition S (+) p rounds to a multiple of q = 2^(e-52), and (ties aside)
+//   S (+) p - S = rne_q(p) does not depend on S.  So the increment a chunk of
+//   1024 terms adds, D = (A (+) p_0 (+) ... (+) p_1023) - A, is the same for
+//   any start A in that binade -- in particular for an approximate prefix A
+//   from a parallel scan and for the true sequential S.
+// Kernel 3 computes D for every chunk from the approximate prefix (twice,
+// from A and from nextafter(A): the two runs have opposite parity, so they
+// disagree exactly when a round-half-even tie occurred); kernel 4 walks the
+// chunks in order with one addition each (exact: all values are multiples of
+// q) and replays a chunk term by term only when a flag says the shortcut is
+// unsafe (tie, binade crossing, wrong binade guess).  The result is the
+// reference's sequence of partial sums, bit for bit, at chunk boundaries;
+// the sampler then replays inside one chunk per shot.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.h"
+#include "gate_math.cuh"
+#include "kernels.h"
+
+namespace qcs {
+
+namespace {
+
+constexpr int RB = 256;  // reduction block size
+
+__device__ __forceinline__ double norm_sq(double2 a) {
+  return __dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y));  // c_norm_sq, complex.c:89-93
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int exponent_of(double x) {
+  return (__double2hiint(x) >> 20) & 0x7ff;
+}
+
+unsigned grid_for(uint64_t items, int per_block) {
+  uint64_t b = (items + per_block - 1) / per_block;
+  if (b > REDUCE_MAX_BLOCKS) b = REDUCE_MAX_BLOCKS;
+  if (b == 0) b = 1;
+  return (unsigned)b;
+}
+
+// ---------------------------------------------------------------- fill / init
+__global__ void init_state_kernel(double2 *state, uint64_t n, int set_one) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    state[i] = make_double2((set_one && i == 0) ? 1.0 : 0.0, 0.0);
+}
+
+// ---------------------------------------------------------------- complex sum
+__global__ void __launch_bounds__(RB) complex_sum_kernel(const double2 *__restrict__ state,
+                                                         uint64_t n, double *partials) {
+  double sr = 0.0, si = 0.0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double2 a = __ldcs(state + i);
+    sr += a.x;
+    si += a.y;
+  }
+  __shared__ double sh[2][RB / 32];
+  sr = warp_sum(sr);
+  si = warp_sum(si);
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = sr;
+    sh[1][threadIdx.x >> 5] = si;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tr = 0.0, ti = 0.0;
+    for (int w = 0; w < RB / 32; w++) {
+      tr += sh[0][w];
+      ti += sh[1][w];
+    }
+    partials[2 * blockIdx.x] = tr;
+    partials[2 * blockIdx.x + 1] = ti;
+  }
+}
+
+__global__ void __launch_bounds__(1024) complex_sum_final_kernel(const double *partials, int nb,
+                                                                 double *result) {
+  double sr = 0.0, si = 0.0;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    sr += partials[2 * b];
+    si += partials[2 * b + 1];
+  }
+  __shared__ double sh[2][32];
+  sr = warp_sum(sr);
+  si = warp_sum(si);
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = sr;
+    sh[1][threadIdx.x >> 5] = si;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tr = 0.0, ti = 0.0;
+    for (int w = 0; w < 32; w++) {
+      tr += sh[0][w];
+      ti += sh[1][w];
+    }
+    result[0] = tr;
+    result[1] = ti;
+  }
+}
+
+// ---------------------------------------------------------------- streaming writes
+// mean of q_apply_diffusion (q_gates.c:337-346) from the raw sum, on the device
+// so that Grover iterations never synchronise with the host.  sqrt and / are
+// IEEE correctly rounded in double, like the host's.
+__global__ void diffusion_mean_kernel(double *result, int corrected, double n_total) {
+  double sr = result[0], si = result[1];
+  if (corrected) {
+    sr = __ddiv_rn(sr, n_total);
+    si = __ddiv_rn(si, n_total);
+  } else {
+    const double mag = __dsqrt_rn(__dadd_rn(__dmul_rn(sr, sr), __dmul_rn(si, si)));
+    if (mag > 1e-10) {
+      sr = __ddiv_rn(sr, mag);
+      si = __ddiv_rn(si, mag);
+    }
+  }
+  result[2] = __dmul_rn(2.0, sr);
+  result[3] = __dmul_rn(2.0, si);
+}
+
+__global__ void __launch_bounds__(256)
+diffusion_write_kernel(const double2 *src, double2 *dst, uint64_t n,
+                       const double *__restrict__ two_mean) {
+  const double tr = two_mean[0], ti = two_mean[1];
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double2 a = __ldcs(src + i);
+    __stcs(dst + i, make_double2(__dsub_rn(tr, a.x), __dsub_rn(ti, a.y)));
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_kernel(double2 *state, uint64_t n, double f) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double2 a = __ldcs(state + i);
+    __stcs(state + i, make_double2(__dmul_rn(a.x, f), __dmul_rn(a.y, f)));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zero_half_kernel(double2 *state, uint64_t n_items, int pos, uint64_t zero_bit) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
+    const uint64_t low = it & ((1ull << pos) - 1ull);
+    const uint64_t i = (((it >> pos) << (pos + 1)) | low) | zero_bit;
+    state[i] = make_double2(0.0, 0.0);
+  }
+}
+
+__global__ void negate_one_kernel(double2 *dst, const double2 *src, uint64_t index) {
+  const double2 a = src[index];
+  dst[index] = make_double2(-a.x, -a.y);
+}
+
+// ---------------------------------------------------------------- argmax
+struct Best {
+  double p;
+  long long idx;
+};
+__device__ __forceinline__ Best better(Best a, Best b) {
+  if (b.p > a.p || (b.p == a.p && b.idx < a.idx)) return b;
+  return a;
+}
+__device__ __forceinline__ Best warp_best(Best v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best w;
+    w.p = __shfl_xor_sync(0xffffffffu, v.p, o);
+    w.idx = __shfl_xor_sync(0xffffffffu, v.idx, o);
+    v = better(v, w);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(RB) argmax_kernel(const double2 *__restrict__ state, uint64_t n,
+                                                    double *partials, long long *ipartials) {
+  Best b{0.0, 0x7fffffffffffffffll};
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double p = norm_sq(__ldcs(state + i));
+    if (p > b.p) {  // strict: first maximum wins (qcs.c:472)
+      b.p = p;
+      b.idx = (long long)i;
+    }
+  }
+  __shared__ double shp[RB / 32];
+  __shared__ long long shi[RB / 32];
+  b = warp_best(b);
+  if ((threadIdx.x & 31) == 0) {
+    shp[threadIdx.x >> 5] = b.p;
+    shi[threadIdx.x >> 5] = b.idx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Best t{shp[0], shi[0]};
+    for (int w = 1; w < RB / 32; w++) t = better(t, Best{shp[w], shi[w]});
+    partials[blockIdx.x] = t.p;
+    ipartials[blockIdx.x] = t.idx;
+  }
+}
+
+__global__ void argmax_final_kernel(const double *partials, const long long *ipartials, int nb,
+                                    double *result, long long *iresult) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    Best t{0.0, 0x7fffffffffffffffll};
+    for (int b = 0; b < nb; b++) t = better(t, Best{partials[b], ipartials[b]});
+    result[0] = t.p;
+    iresult[0] = (t.p > 0.0) ? t.idx : 0;  // all-zero state -> 0 (qcs.c:465-466)
+  }
+}
+
+// ---------------------------------------------------------------- exact prefix
+enum { FLAG_TIE = 1, FLAG_CROSS = 2, FLAG_ZERO = 4 };
+
+__device__ __forceinline__ double masked_norm(const double2 *__restrict__ state, uint64_t i,
+                                              int mask_pos) {
+  if (mask_pos >= 0 && ((i >> mask_pos) & 1ull)) return 0.0;
+  return norm_sq(__ldg(state + i));
+}
+
+// K1: plain (tree) sum of each 1024-term chunk; one warp per chunk.
+__global__ void __launch_bounds__(256)
+chunk_sum_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mask_pos,
+                 double *chunk_sum) {
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t c = warp; c < n_chunks; c += n_warps) {
+    double s = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < SEQ_CHUNK / 32; j++)
+      s += masked_norm(state, c * SEQ_CHUNK + (uint64_t)j * 32 + lane, mask_pos);
+    s = warp_sum(s);
+    if (lane == 0) chunk_sum[c] = s;
+  }
+}
+
+// K2: approximate exclusive prefix over chunks (single block, 1024 threads).
+__global__ void __launch_bounds__(1024)
+chunk_scan_kernel(const double *chunk_sum, uint64_t n_chunks, const double *start_dev,
+                  double *approx) {
+  const double start = *start_dev;
+  __shared__ double sh[1024];
+  const uint64_t per = (n_chunks + 1023) / 1024;
+  const uint64_t lo = (uint64_t)threadIdx.x * per;
+  const uint64_t hi = lo + per < n_chunks ? lo + per : n_chunks;
+  double s = 0.0;
+  for (uint64_t c = lo; c < hi; c++) s += chunk_sum[c];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double run = start;
+    for (int t = 0; t < 1024; t++) {
+      const double v = sh[t];
+      sh[t] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  double run = sh[threadIdx.x];
+  for (uint64_t c = lo; c < hi; c++) {
+    approx[c] = run;
+    run += chunk_sum[c];
+  }
+}
+
+// K3: per-chunk increment D and safety flags.  One warp handles 32 chunks;
+// 32x32 blocks of |a|^2 are staged through shared memory so global loads stay
+// coalesced while each lane walks ITS chunk strictly left to right.
+__global__ void __launch_bounds__(128)
+chunk_delta_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mask_pos,
+                   const double *__restrict__ chunk_sum, const double *__restrict__ approx,
+                   double *__restrict__ delta, unsigned char *__restrict__ flag) {
+  __shared__ double stage[4][32][33];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const uint64_t group = (uint64_t)blockIdx.x * 4 + wib;  // 32 chunks per group
+  const uint64_t c0 = group * 32;
+  if (c0 >= n_chunks) return;
+  const uint64_t my_chunk = c0 + lane;
+  const bool have = my_chunk < n_chunks;
+  const double csum = have ? chunk_sum[my_chunk] : 0.0;
+  const bool any_work = __any_sync(0xffffffffu, have && csum != 0.0);
+  if (!any_work) {
+    if (have) {
+      delta[my_chunk] = 0.0;
+      flag[my_chunk] = FLAG_ZERO;
+    }
+    return;
+  }
+  const double a1 = have ? approx[my_chunk] : 1.0;
+  const double a2 = __longlong_as_double(__double_as_longlong(a1) + 1);  // next double up (a1 >= 0)
+  double s1 = a1, s2 = a2;
+  const int n_rows = (int)((n_chunks - c0) < 32 ? (n_chunks - c0) : 32);
+  for (int j = 0; j < SEQ_CHUNK / 32; j++) {
+#pragma unroll 8
+    for (int c = 0; c < 32; c++) {
+      double p = 0.0;
+      if (c < n_rows)
+        p = masked_norm(state, (c0 + c) * SEQ_CHUNK + (uint64_t)j * 32 + lane, mask_pos);
+      stage[wib][c][lane] = p;
+    }
+    __syncwarp();
+#pragma unroll 8
+    for (int k = 0; k < 32; k++) {
+      const double p = stage[wib][lane][k];
+      s1 = __dadd_rn(s1, p);
+      s2 = __dadd_rn(s2, p);
+    }
+    __syncwarp();
+  }
+  if (have) {
+    const double d1 = __dsub_rn(s1, a1);
+    const double d2 = __dsub_rn(s2, a2);
+    unsigned char f = 0;
+    if (csum == 0.0) f |= FLAG_ZERO;
+    if (d1 != d2) f |= FLAG_TIE;
+    if (exponent_of(s1) != exponent_of(a1) || exponent_of(s2) != exponent_of(a1)) f |= FLAG_CROSS;
+    delta[my_chunk] = d1;
+    flag[my_chunk] = f;
+  }
+}
+
+// Term-by-term replay of one chunk by a full warp (all lanes keep the same S).
+__device__ __forceinline__ double replay_chunk(const double2 *__restrict__ state, uint64_t first,
+                                               uint64_t len, int mask_pos, double S, int lane) {
+  for (uint64_t j = 0; j < len; j += 32) {
+    const uint64_t i = first + j + lane;
+    const double p = (j + lane < len) ? masked_norm(state, i, mask_pos) : 0.0;
+#pragma unroll
+    for (int l = 0; l < 32; l++) S = __dadd_rn(S, __shfl_sync(0xffffffffu, p, l));
+  }
+  return S;
+}
+
+// K4: walk the chunks in order (one warp; every lane carries the same S).
+__global__ void __launch_bounds__(32)
+chunk_resolve_kernel(const double2 *__restrict__ state, uint64_t n_amps, uint64_t n_chunks,
+                     uint64_t chunk_len, int mask_pos, const double *start_dev,
+                     const double *__restrict__ approx, const double *__restrict__ delta,
+                     const unsigned char *__restrict__ flag, int have_deltas,
+                     double *__restrict__ exact, double *total_out, long long *replays) {
+  const int lane = threadIdx.x;
+  double S = *start_dev;
+  long long n_replay = 0;
+  for (uint64_t base = 0; base < n_chunks; base += 32) {
+    const uint64_t mine = base + lane;
+    double my_d = 0.0, my_a = 0.0;
+    int my_f = FLAG_CROSS;
+    if (have_deltas && mine < n_chunks) {
+      my_d = delta[mine];
+      my_a = approx[mine];
+      my_f = flag[mine];
+    }
+    double my_exact = 0.0;
+    const int lim = (int)((n_chunks - base) < 32 ? (n_chunks - base) : 32);
+    for (int j = 0; j < lim; j++) {
+      const double d = __shfl_sync(0xffffffffu, my_d, j);
+      const double a = __shfl_sync(0xffffffffu, my_a, j);
+      const int f = __shfl_sync(0xffffffffu, my_f, j);
+      if (lane == j) my_exact = S;
+      if (f & FLAG_ZERO) continue;
+      bool ok = !(f & (FLAG_TIE | FLAG_CROSS)) && exponent_of(S) == exponent_of(a);
+      double Snew = S;
+      if (ok) {
+        Snew = __dadd_rn(S, d);
+        ok = exponent_of(Snew) == exponent_of(S);
+      }
+      if (ok) {
+        S = Snew;
+      } else {
+        S = replay_chunk(state, (base + j) * chunk_len, chunk_len, mask_pos, S, lane);
+        n_replay++;
+      }
+    }
+    if (mine < n_chunks) exact[mine] = my_exact;
+  }
+  if (lane == 0) {
+    exact[n_chunks] = S;
+    *total_out = S;
+    if (replays) *replays = n_replay;
+  }
+  (void)n_amps;
+}
+
+// Total of the chunk sums (approximate shard total, for cross-rank offsets).
+__global__ void __launch_bounds__(1024)
+chunk_total_kernel(const double *chunk_sum, uint64_t n_chunks, double *out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (uint64_t c = threadIdx.x; c < n_chunks; c += blockDim.x) s += chunk_sum[c];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; w++) t += sh[w];
+    *out = t;
+  }
+}
+
+// K5: one thread per shot.
+__global__ void __launch_bounds__(128)
+sample_kernel(const double2 *__restrict__ state, uint64_t n_chunks, uint64_t chunk_len,
+              const double *__restrict__ exact, const double *__restrict__ u_dev, int shots,
+              long long *__restrict__ idx_out, long long index_offset) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= shots) return;
+  const double u = u_dev[k];
+  long long found = -1;
+  // Not ours if an earlier shard already satisfied u < sum, or no prefix here exceeds u.
+  if (!(u < exact[0]) && (u < exact[n_chunks])) {
+    // smallest c with u < exact[c + 1]
+    uint64_t lo = 0, hi = n_chunks - 1;
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (u < exact[mid + 1]) hi = mid; else lo = mid + 1;
+    }
+    double S = exact[lo];
+    const uint64_t first = lo * chunk_len;
+    for (uint64_t i = 0; i < chunk_len; i++) {
+      S = __dadd_rn(S, norm_sq(__ldg(state + first + i)));
+      if (u < S) {  // strict, qcs.c:600
+        found = (long long)(first + i) + index_offset;
+        break;
+      }
+    }
+  }
+  idx_out[k] = found;
+}
+
+}  // namespace
+
+// =============================================================== launchers
+cudaError_t launch_init_state(double2 *state, uint64_t n, bool set_one, cudaStream_t s) {
+  init_state_kernel<<<grid_for(n, 256 * 8), 256, 0, s>>>(state, n, set_one ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_complex_sum(const double2 *state, uint64_t n, ReduceWorkspace &ws,
+                               cudaStream_t s) {
+  const unsigned nb = grid_for(n, RB * 8);
+  complex_sum_kernel<<<nb, RB, 0, s>>>(state, n, ws.partials);
+  complex_sum_final_kernel<<<1, 1024, 0, s>>>(ws.partials, (int)nb, ws.result);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_diffusion_mean(ReduceWorkspace &ws, bool corrected, double n_total,
+                                  cudaStream_t s) {
+  diffusion_mean_kernel<<<1, 1, 0, s>>>(ws.result, corrected ? 1 : 0, n_total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_diffusion_write(const double2 *src, double2 *dst, uint64_t n,
+                                   const ReduceWorkspace &ws, cudaStream_t s) {
+  diffusion_write_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(src, dst, n, ws.result + 2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scale(double2 *state, uint64_t n, double f, cudaStream_t s) {
+  scale_kernel<<<grid_for(n, 256 * 4), 256, 0, s>>>(state, n, f);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zero_half(double2 *state, uint64_t n, int pos, int keep_bit, cudaStream_t s) {
+  const uint64_t items = n >> 1;
+  const uint64_t zero_bit = keep_bit ? 0ull : (1ull << pos);
+  zero_half_kernel<<<grid_for(items, 256 * 4), 256, 0, s>>>(state, items, pos, zero_bit);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_negate_one(double2 *dst, const double2 *src, uint64_t index, cudaStream_t s) {
+  negate_one_kernel<<<1, 1, 0, s>>>(dst, src, index);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_argmax(const double2 *state, uint64_t n, ReduceWorkspace &ws, cudaStream_t s) {
+  const unsigned nb = grid_for(n, RB * 8);
+  argmax_kernel<<<nb, RB, 0, s>>>(state, n, ws.partials, ws.ipartials);
+  argmax_final_kernel<<<1, 32, 0, s>>>(ws.partials, ws.ipartials, (int)nb, ws.result, ws.iresult);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chunk_sums(const double2 *state, uint64_t n, int mask_pos,
+                              ReduceWorkspace &ws, cudaStream_t s) {
+  if (n < (uint64_t)SEQ_CHUNK) return cudaSuccess;  // single short chunk: resolved by replay
+  const uint64_t n_chunks = n / SEQ_CHUNK;
+  uint64_t blocks = (n_chunks + 7) / 8;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  chunk_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(state, n_chunks, mask_pos, ws.chunk_sum);
+  chunk_total_kernel<<<1, 1024, 0, s>>>(ws.chunk_sum, n_chunks, ws.result + RES_APPROX_TOTAL);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chunk_deltas(const double2 *state, uint64_t n, int mask_pos,
+                                const double *approx_start_dev, ReduceWorkspace &ws,
+                                cudaStream_t s) {
+  if (n < (uint64_t)SEQ_CHUNK) return cudaSuccess;
+  const uint64_t n_chunks = n / SEQ_CHUNK;
+  chunk_scan_kernel<<<1, 1024, 0, s>>>(ws.chunk_sum, n_chunks, approx_start_dev, ws.chunk_approx);
+  const uint64_t groups = (n_chunks + 31) / 32;
+  const uint64_t blocks = (groups + 3) / 4;
+  chunk_delta_kernel<<<(unsigned)blocks, 128, 0, s>>>(state, n_chunks, mask_pos, ws.chunk_sum,
+                                                      ws.chunk_approx, ws.chunk_delta,
+                                                      ws.chunk_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chunk_resolve(const double2 *state, uint64_t n, int mask_pos,
+                                 const double *exact_start_dev, ReduceWorkspace &ws,
+                                 cudaStream_t s) {
+  if (n < (uint64_t)SEQ_CHUNK) {
+    chunk_resolve_kernel<<<1, 32, 0, s>>>(state, n, 1, n, mask_pos, exact_start_dev, nullptr,
+                                          nullptr, nullptr, 0, ws.chunk_exact,
+                                          ws.result + RES_EXACT_TOTAL, ws.iresult + 1);
+    return cudaGetLastError();
+  }
+  const uint64_t n_chunks = n / SEQ_CHUNK;
+  chunk_resolve_kernel<<<1, 32, 0, s>>>(state, n, n_chunks, SEQ_CHUNK, mask_pos, exact_start_dev,
+                                        ws.chunk_approx, ws.chunk_delta, ws.chunk_flag, 1,
+                                        ws.chunk_exact, ws.result + RES_EXACT_TOTAL,
+                                        ws.iresult + 1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample(const double2 *state, uint64_t n, const ReduceWorkspace &ws,
+                          const double *u_dev, int shots, long long *idx_dev,
+                          long long index_offset, cudaStream_t s) {
+  const uint64_t chunk_len = n < (uint64_t)SEQ_CHUNK ? n : (uint64_t)SEQ_CHUNK;
+  const uint64_t n_chunks = n / chunk_len;
+  sample_kernel<<<(shots + 127) / 128, 128, 0, s>>>(state, n_chunks, chunk_len, ws.chunk_exact,
+                                                    u_dev, shots, idx_dev, index_offset);
+  return cudaGetLastError();
+}
+
+}  // namespace qcs

@@ -1,0 +1,92 @@
+// kernels_simple.cu -- one launch per gate, in place.
+//
+// The unfused path: used when QCS_CUDA_FUSION=off (parity cross-check of the
+// fused scheduler) and for shards smaller than one tile (fewer than 12 local
+// qubits).  Direct counterpart of the reference's per-gate sweeps
+// (q_apply_1q_gate reference src/q_gates.c:131-143, q_apply_2q_gate :276-292),
+// minus the memcpy: every pair is read once and written once.
+// Algorithmic bytes: 32 * 2^nl (uncontrolled), 16 * 2^nl (controlled pairing),
+// 8..16 * 2^nl (diagonal) -- SURVEY.md section 8(d).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.h"
+#include "gate_math.cuh"
+#include "kernels.h"
+
+namespace qcs {
+
+namespace {
+
+__device__ __forceinline__ uint64_t insert_zero(uint64_t v, int pos) {
+  const uint64_t low = v & ((1ull << pos) - 1ull);
+  return ((v >> pos) << (pos + 1)) | low;
+}
+
+__global__ void __launch_bounds__(256)
+simple_pair_kernel(double2 *__restrict__ state, const __grid_constant__ DGate g,
+                   int local_control, uint64_t n_items) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < n_items;
+       item += stride) {
+    uint64_t i0;
+    if (local_control) {
+      const int lo = g.tpos < g.cpos ? g.tpos : g.cpos;
+      const int hi = g.tpos < g.cpos ? g.cpos : g.tpos;
+      i0 = insert_zero(insert_zero(item, lo), hi) | (1ull << g.cpos);
+    } else {
+      i0 = insert_zero(item, g.tpos);
+    }
+    const uint64_t i1 = i0 | (1ull << g.tpos);
+    double2 v0 = state[i0];
+    double2 v1 = state[i1];
+    pair_update(g, v0.x, v0.y, v1.x, v1.y);
+    state[i0] = v0;
+    if (!(g.flags & GF_ROW0_ONLY)) state[i1] = v1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+simple_diag_kernel(double2 *__restrict__ state, const __grid_constant__ DGate g,
+                   uint64_t shard_base, uint64_t n_amps) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps; i += stride) {
+    const uint64_t full = shard_base | i;
+    if (g.cpos >= 0 && !bit_of(full, g.cpos)) continue;
+    const bool t = bit_of(full, g.tpos);
+    if (t ? (g.flags & GF_D1_IDENT) : (g.flags & GF_D0_IDENT)) continue;
+    const double2 v = state[i];
+    const cplx n = cmul(t ? g.m[6] : g.m[0], t ? g.m[7] : g.m[1], v.x, v.y);
+    state[i] = make_double2(n.r, n.i);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_simple_gate(double2 *state, const DGate &g, int n_local, uint64_t shard_base,
+                               cudaStream_t stream) {
+  if (g.kind == GK_NOP) return cudaSuccess;
+  const uint64_t n_amps = 1ull << n_local;
+  if (g.kind == GK_DIAG) {
+    const unsigned blocks = (unsigned)((n_amps + 255) / 256 > 148 * 16 ? 148 * 16 : (n_amps + 255) / 256);
+    simple_diag_kernel<<<blocks, 256, 0, stream>>>(state, g, shard_base, n_amps);
+    return cudaGetLastError();
+  }
+  // pairing gate: the target must be local (the engine remaps first otherwise)
+  int local_control = 0;
+  uint64_t n_items = n_amps >> 1;
+  if (g.cpos >= 0) {
+    if (g.cpos >= n_local) {
+      if (!((shard_base >> g.cpos) & 1ull)) return cudaSuccess;  // control bit is 0 on this rank
+    } else {
+      local_control = 1;
+      n_items = n_amps >> 2;
+    }
+  }
+  if (n_items == 0) n_items = 1;  // 1-qubit shard with a local control cannot happen; guard anyway
+  const unsigned blocks = (unsigned)((n_items + 255) / 256 > 148 * 16 ? 148 * 16 : (n_items + 255) / 256);
+  simple_pair_kernel<<<blocks, 256, 0, stream>>>(state, g, local_control, n_items);
+  return cudaGetLastError();
+}
+
+}  // namespace qcs

@@ -1,0 +1,353 @@
+// planner.cpp -- see planner.h.  Pure host code.
+#include "planner.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace qcs {
+
+static inline bool is_zero(double x) { return x == 0.0; }  // true for -0.0 too
+static inline bool is_one_c(const double *c) { return c[0] == 1.0 && is_zero(c[1]); }
+static inline bool is_zero_c(const double *c) { return is_zero(c[0]) && is_zero(c[1]); }
+
+Classified classify_gate(const double m[8], bool controlled, Semantics sem) {
+  Classified r;
+  std::memcpy(r.m, m, sizeof(r.m));
+  r.flags = 0;
+  const double *g0 = m, *g1 = m + 2, *g2 = m + 4, *g3 = m + 6;
+  const double ctrl_frac = controlled ? 0.5 : 1.0;
+
+  if (controlled && sem == SEM_REFERENCE) {
+    // As written in the reference (src/q_gates.c:276-292, defect D1) only the
+    // target=0 member of a control=1 pair changes: n0 = g0*v0 + g1*v1.
+    r.flags |= GF_ROW0_ONLY;
+    if (is_zero_c(g1)) {
+      // n0 = g0*v0 (+ exact zero): elementwise on the target=0 element.
+      r.m[2] = r.m[3] = r.m[4] = r.m[5] = 0.0;
+      r.m[6] = 1.0;
+      r.m[7] = 0.0;
+      r.flags |= GF_D1_IDENT;
+      if (is_one_c(g0)) {
+        r.kind = GK_NOP;  // e.g. CPHASE under reference semantics
+        r.flags |= GF_D0_IDENT;
+        r.flops_per_amp = 0.0;
+      } else {
+        r.kind = GK_DIAG;
+        r.flops_per_amp = 6.0 * 0.25;
+      }
+      return r;
+    }
+  } else if (is_zero_c(g1) && is_zero_c(g2)) {
+    r.kind = GK_DIAG;
+    if (is_one_c(g0)) r.flags |= GF_D0_IDENT;
+    if (is_one_c(g3)) r.flags |= GF_D1_IDENT;
+    int touched = ((r.flags & GF_D0_IDENT) ? 0 : 1) + ((r.flags & GF_D1_IDENT) ? 0 : 1);
+    if (touched == 0) r.kind = GK_NOP;
+    r.flops_per_amp = 6.0 * 0.5 * touched * ctrl_frac;
+    return r;
+  }
+
+  const bool all_real = is_zero(m[1]) && is_zero(m[3]) && is_zero(m[5]) && is_zero(m[7]);
+  if (all_real && is_zero(g0[0]) && is_zero(g3[0]) && g1[0] == 1.0 && g2[0] == 1.0) {
+    r.kind = GK_PAIR_SWAP;
+    r.flops_per_amp = 0.5 * ctrl_frac;
+  } else if (all_real && g0[0] == g2[0] && g3[0] == -g1[0]) {
+    r.kind = GK_PAIR_HSYM;
+    r.flops_per_amp = 4.0 * ctrl_frac;
+  } else if (all_real) {
+    r.kind = GK_PAIR_REAL;
+    r.flops_per_amp = 6.0 * ctrl_frac;
+  } else {
+    r.kind = GK_PAIR_GENERIC;
+    r.flops_per_amp = 14.0 * ctrl_frac;
+  }
+  if (r.flags & GF_ROW0_ONLY) r.flops_per_amp *= 0.5;
+  return r;
+}
+
+static bool is_pairing(uint8_t kind) {
+  return kind == GK_PAIR_GENERIC || kind == GK_PAIR_REAL || kind == GK_PAIR_HSYM ||
+         kind == GK_PAIR_SWAP;
+}
+
+// Assigns the 12 tile bits to roles for one segment.  `regbits` (tile-bit
+// indices) become the register roles; of the rest, three bits with distinct
+// residues mod 3 become lane bits 0..2 so that, with the XOR swizzle used by
+// the kernel (slot ^ (slot>>3) ^ (slot>>6) ^ (slot>>9) on the low 3 bits),
+// every quarter-warp of a 16-byte shared-memory access hits 8 distinct bank
+// groups.  With no register bit below 5 this yields lane bits = tile bits
+// 0..4, i.e. fully coalesced 512-byte global rows per warp.
+static void assign_roles(const std::vector<int> &regbits, uint8_t role_tilebit[QCS_TILE_BITS]) {
+  bool is_reg[QCS_TILE_BITS] = {false};
+  for (int b : regbits) is_reg[b] = true;
+  std::vector<int> rest;
+  for (int b = 0; b < QCS_TILE_BITS; b++)
+    if (!is_reg[b]) rest.push_back(b);
+  std::vector<int> lane_lo;
+  bool used_res[3] = {false, false, false};
+  bool taken[QCS_TILE_BITS] = {false};
+  for (int b : rest) {
+    if ((int)lane_lo.size() < 3 && !used_res[b % 3]) {
+      lane_lo.push_back(b);
+      used_res[b % 3] = true;
+      taken[b] = true;
+    }
+  }
+  for (int b : rest) {
+    if ((int)lane_lo.size() < 3 && !taken[b]) {
+      lane_lo.push_back(b);
+      taken[b] = true;
+    }
+  }
+  int role = 0;
+  for (int b : lane_lo) role_tilebit[role++] = (uint8_t)b;
+  for (int b : rest)
+    if (!taken[b]) role_tilebit[role++] = (uint8_t)b;  // lane 3,4 then warp 0..2
+  for (int b : regbits) role_tilebit[role++] = (uint8_t)b;
+}
+
+namespace {
+
+struct PassBuilder {
+  const PlannerConfig &cfg;
+  std::vector<int> tile;          // physical positions in the tile (unsorted until close)
+  std::vector<PhysGate> gates;
+  int n_api = 0;
+  double flops = 0.0;
+
+  explicit PassBuilder(const PlannerConfig &c) : cfg(c) {
+    for (int p = 0; p < QCS_LANE_BITS; p++) tile.push_back(p);
+  }
+  bool has(int pos) const { return std::find(tile.begin(), tile.end(), pos) != tile.end(); }
+  bool empty() const { return gates.empty() && n_api == 0; }
+
+  // Counts the segments the current gate list needs (plus the I/O segments).
+  int segments_needed(const PhysGate *extra) const {
+    int segs = 1, in_r = 0;
+    int r[QCS_MAX_REG_BITS];
+    bool first_low = false, last_low = false;
+    auto feed = [&](const PhysGate &g) {
+      if (!is_pairing(g.c.kind)) return;
+      for (int k = 0; k < in_r; k++)
+        if (r[k] == g.tpos) return;
+      if (in_r == cfg.reg_bits) {
+        segs++;
+        in_r = 0;
+        last_low = false;
+      }
+      r[in_r++] = g.tpos;
+      if (g.tpos < QCS_LANE_BITS) {
+        if (segs == 1) first_low = true;
+        last_low = true;
+      }
+    };
+    for (const auto &g : gates) feed(g);
+    if (extra) feed(*extra);
+    if (cfg.direct_io) segs += (first_low ? 1 : 0) + (last_low ? 1 : 0);
+    return segs;
+  }
+
+  bool fits(const PhysGate &g) const {
+    if ((int)gates.size() + 1 > QCS_MAX_PASS_GATES) return false;
+    if (!gates.empty() && flops + g.c.flops_per_amp > cfg.pass_flops_budget) return false;
+    if (is_pairing(g.c.kind) && !has(g.tpos) && (int)tile.size() >= QCS_TILE_BITS) return false;
+    if (segments_needed(&g) > QCS_MAX_PASS_SEGMENTS) return false;
+    return true;
+  }
+
+  void add(const PhysGate &g) {
+    n_api++;
+    if (g.c.kind == GK_NOP) return;
+    if (is_pairing(g.c.kind) && !has(g.tpos)) tile.push_back(g.tpos);
+    gates.push_back(g);
+    flops += g.c.flops_per_amp;
+  }
+
+  PassPlan close() {
+    PassPlan plan;
+    std::memset(&plan.params, 0, sizeof(plan.params));
+    // Fill the tile with the lowest unused local positions (keeps rows long).
+    for (int p = QCS_LANE_BITS; (int)tile.size() < QCS_TILE_BITS && p < cfg.n_local; p++)
+      if (!has(p)) tile.push_back(p);
+    std::sort(tile.begin(), tile.end());
+    plan.tile_positions = tile;
+    PassParams &pp = plan.params;
+    pp.shard_base = cfg.shard_base;
+    uint64_t tile_mask = 0;
+    for (int b = 0; b < QCS_TILE_BITS; b++) {
+      pp.tile_pos[b] = (uint8_t)tile[b];
+      tile_mask |= 1ull << tile[b];
+    }
+    pp.nontile_mask = ((cfg.n_local >= 64 ? ~0ull : ((1ull << cfg.n_local) - 1))) & ~tile_mask;
+    auto tilebit_of = [&](int pos) -> int {
+      for (int b = 0; b < QCS_TILE_BITS; b++)
+        if (tile[b] == pos) return b;
+      return -1;
+    };
+
+    // Cut into segments: a segment's register set grows on demand up to 4 bits.
+    struct Seg { std::vector<int> regbits; int begin, end; };
+    std::vector<Seg> segs;
+    segs.push_back(Seg{{}, 0, 0});
+    for (int gi = 0; gi < (int)gates.size(); gi++) {
+      const PhysGate &g = gates[gi];
+      if (is_pairing(g.c.kind)) {
+        int tb = tilebit_of(g.tpos);
+        Seg &cur = segs.back();
+        if (std::find(cur.regbits.begin(), cur.regbits.end(), tb) == cur.regbits.end()) {
+          if ((int)cur.regbits.size() == cfg.reg_bits) {
+            cur.end = gi;
+            segs.push_back(Seg{{tb}, gi, gi});
+          } else {
+            cur.regbits.push_back(tb);
+          }
+        }
+      }
+      segs.back().end = gi + 1;
+    }
+    // Complete register sets with spare tile bits (highest first, never below 5
+    // unless forced) so that lanes keep the low bits.
+    for (auto &s : segs) {
+      for (int b = QCS_TILE_BITS - 1; b >= 0 && (int)s.regbits.size() < cfg.reg_bits; b--)
+        if (std::find(s.regbits.begin(), s.regbits.end(), b) == s.regbits.end())
+          s.regbits.push_back(b);
+    }
+    if (cfg.direct_io) {
+      auto low = [](const Seg &s) {
+        for (int b : s.regbits)
+          if (b < QCS_LANE_BITS) return true;
+        return false;
+      };
+      std::vector<int> io_regs;
+      for (int k = cfg.reg_bits; k >= 1; k--) io_regs.push_back(QCS_TILE_BITS - k);
+      if (low(segs.front())) segs.insert(segs.begin(), Seg{io_regs, 0, 0});
+      if (low(segs.back())) {
+        int e = (int)gates.size();
+        segs.push_back(Seg{io_regs, e, e});
+      }
+    }
+    pp.n_segments = (int)segs.size();
+    pp.n_gates = (int)gates.size();
+    pp.reg_bits = cfg.reg_bits;
+    for (int si = 0; si < (int)segs.size(); si++) {
+      DSegment &ds = pp.seg[si];
+      assign_roles(segs[si].regbits, ds.role_tilebit);
+      ds.gate_begin = (uint16_t)segs[si].begin;
+      ds.gate_end = (uint16_t)segs[si].end;
+      for (int gi = segs[si].begin; gi < segs[si].end; gi++) {
+        const PhysGate &g = gates[gi];
+        DGate &dg = pp.gate[gi];
+        std::memcpy(dg.m, g.c.m, sizeof(dg.m));
+        dg.kind = g.c.kind;
+        dg.flags = g.c.flags;
+        dg.tpos = (int8_t)g.tpos;
+        dg.cpos = (int8_t)g.cpos;
+        int treg = -1, creg = -1;
+        int tb = tilebit_of(g.tpos);
+        int cb = g.cpos >= 0 ? tilebit_of(g.cpos) : -1;
+        for (int k = 0; k < cfg.reg_bits; k++) {
+          if (tb >= 0 && segs[si].regbits[k] == tb) treg = k;
+          if (cb >= 0 && segs[si].regbits[k] == cb) creg = k;
+        }
+        dg.treg_creg = (int8_t)((treg + 1) | ((creg + 1) << 4));
+        // A bit that is not a register bit is tested once per thread (lane / warp
+        // tile bits: encoded as the tile-bit index) or once per tile (positions
+        // outside the tile: QCS_SEL_OUTSIDE | physical position).
+        auto encode_sel = [&](int pos, int tilebit) -> uint8_t {
+          return tilebit >= 0 ? (uint8_t)tilebit : (uint8_t)(QCS_SEL_OUTSIDE | pos);
+        };
+        dg.ctest = (g.cpos >= 0 && creg < 0) ? encode_sel(g.cpos, cb) : 0xFF;
+        dg.tsel = 0xFF;
+        const int row0 = (g.c.flags & GF_ROW0_ONLY) ? 1 : 0;
+        switch (g.c.kind) {
+          case GK_PAIR_HSYM: dg.op = (uint8_t)qcs_op_id_pair(0, row0, treg, creg); break;
+          case GK_PAIR_REAL: dg.op = (uint8_t)qcs_op_id_pair(1, row0, treg, creg); break;
+          case GK_PAIR_SWAP: dg.op = (uint8_t)qcs_op_id_pair(2, row0, treg, creg); break;
+          case GK_PAIR_GENERIC: dg.op = (uint8_t)qcs_op_id_pair(3, row0, treg, creg); break;
+          case GK_DIAG:
+            if (treg < 0) {
+              dg.op = (uint8_t)qcs_op_id_diag_free(creg);
+              dg.tsel = encode_sel(g.tpos, tb);
+            } else {
+              const int halves = ((g.c.flags & GF_D0_IDENT) ? 0 : 1) | ((g.c.flags & GF_D1_IDENT) ? 0 : 2);
+              dg.op = halves ? (uint8_t)qcs_op_id_diag_reg(treg, creg, halves) : (uint8_t)QCS_OP_NONE;
+            }
+            break;
+          default: dg.op = QCS_OP_NONE; break;
+        }
+      }
+    }
+    // sentinel header read by the interpreter's one-ahead prefetch
+    std::memset(&pp.gate[gates.size()], 0, sizeof(DGate));
+    pp.gate[gates.size()].op = QCS_OP_NONE;
+    pp.gate[gates.size()].ctest = 0xFF;
+    pp.gate[gates.size()].tsel = 0xFF;
+    plan.n_gates_api = n_api;
+    plan.flops_per_amp = flops;
+    return plan;
+  }
+};
+
+}  // namespace
+
+std::vector<PassPlan> plan_passes(const std::vector<PhysGate> &gates, const PlannerConfig &cfg) {
+  std::vector<PassPlan> out;
+  PassBuilder *b = new PassBuilder(cfg);
+  for (const PhysGate &g : gates) {
+    if (g.c.kind != GK_NOP && !b->fits(g)) {
+      out.push_back(b->close());
+      delete b;
+      b = new PassBuilder(cfg);
+    }
+    b->add(g);
+  }
+  if (!b->gates.empty()) {
+    out.push_back(b->close());
+  } else if (b->n_api > 0 && !out.empty()) {
+    out.back().n_gates_api += b->n_api;  // trailing NOPs ride on the previous pass
+  }
+  delete b;
+  return out;
+}
+
+std::string describe_plan(const std::vector<PassPlan> &passes) {
+  std::string s;
+  char buf[256];
+  static const char *kind_name[] = {"generic", "real", "hsym", "swap", "diag", "nop"};
+  for (size_t pi = 0; pi < passes.size(); pi++) {
+    const PassParams &pp = passes[pi].params;
+    std::snprintf(buf, sizeof(buf), "pass %zu: gates=%d api_gates=%d segments=%d flops/amp=%.1f tile=[",
+                  pi, pp.n_gates, passes[pi].n_gates_api, pp.n_segments, passes[pi].flops_per_amp);
+    s += buf;
+    for (int b = 0; b < QCS_TILE_BITS; b++) {
+      std::snprintf(buf, sizeof(buf), "%s%d", b ? "," : "", pp.tile_pos[b]);
+      s += buf;
+    }
+    s += "]\n";
+    for (int si = 0; si < pp.n_segments; si++) {
+      const DSegment &ds = pp.seg[si];
+      std::snprintf(buf, sizeof(buf), "  seg %d: regs(pos)=[", si);
+      s += buf;
+      for (int k = 0; k < pp.reg_bits; k++) {
+        std::snprintf(buf, sizeof(buf), "%s%d", k ? "," : "",
+                      pp.tile_pos[ds.role_tilebit[QCS_TILE_BITS - pp.reg_bits + k]]);
+        s += buf;
+      }
+      std::snprintf(buf, sizeof(buf), "] gates %d..%d:", ds.gate_begin, ds.gate_end);
+      s += buf;
+      for (int gi = ds.gate_begin; gi < ds.gate_end; gi++) {
+        const DGate &g = pp.gate[gi];
+        if (g.cpos >= 0)
+          std::snprintf(buf, sizeof(buf), " %s(c%d,t%d)", kind_name[g.kind], g.cpos, g.tpos);
+        else
+          std::snprintf(buf, sizeof(buf), " %s(t%d)", kind_name[g.kind], g.tpos);
+        s += buf;
+      }
+      s += "\n";
+    }
+  }
+  return s;
+}
+
+}  // namespace qcs

@@ -1,0 +1,68 @@
+// planner.h -- the gate-fusion scheduler (host side, no CUDA dependency).
+//
+// Replaces the role the north star gives to qc_optimize/qc_run ("a
+// gate-fusion scheduler that batches consecutive gates per pass"); the
+// reference itself applies every gate eagerly with one full sweep per gate
+// (reference src/qcs.c:159-164 -> src/q_gates.c:131-148).  The planner takes
+// the deferred queue and cuts it, IN ORDER, into passes and segments
+// (common.h).  Gates are never reordered or algebraically merged, so the
+// arithmetic each amplitude sees is the reference's, operation by operation.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace qcs {
+
+enum Semantics { SEM_REFERENCE = 0, SEM_CORRECTED = 1 };
+
+// A queued gate in LOGICAL qubit numbering.
+struct HostGate {
+  double m[8];
+  int target;
+  int control;  // -1: uncontrolled
+};
+
+struct Classified {
+  uint8_t kind;
+  uint8_t flags;
+  double m[8];      // possibly normalised copy (identity rows made explicit)
+  double flops_per_amp;
+};
+
+// Classifies a 2x2 (or controlled 2x2) by its exact zero / one pattern.
+Classified classify_gate(const double m[8], bool controlled, Semantics sem);
+
+struct PassPlan {
+  PassParams params;
+  int n_gates_api;          // API-level gates folded into this pass (incl. NOPs)
+  double flops_per_amp;     // planner's cost estimate
+  std::vector<int> tile_positions;
+};
+
+struct PlannerConfig {
+  int n_local;              // local qubits of this shard (nl)
+  int rank_bits;            // log2(world)
+  uint64_t shard_base;      // rank << nl
+  Semantics sem;
+  double pass_flops_budget; // close a pass when its estimated flops/amp exceed this
+  bool direct_io;           // true: first/last segment must keep tile bits 0..4 as lane bits
+  int reg_bits;             // register-role bits per thread: 4 (16 amplitudes) or 3 (8)
+};
+
+// Plans a run of gates whose targets (if pairing) are all LOCAL physical
+// positions.  `phys_target/phys_control` give physical positions (after the
+// logical->physical permutation); controls and diagonal targets may be global.
+struct PhysGate {
+  Classified c;
+  int tpos;
+  int cpos;
+};
+
+std::vector<PassPlan> plan_passes(const std::vector<PhysGate> &gates,
+                                  const PlannerConfig &cfg);
+
+std::string describe_plan(const std::vector<PassPlan> &passes);
+
+}  // namespace qcs

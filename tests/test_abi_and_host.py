@@ -1,0 +1,136 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol
+include/*.h declares; the host layer's bookkeeping (history, num_gates,
+qc_optimize, qc_print_circuit) matches the real reference; the product refuses
+to run without a device instead of falling back."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from oracle import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libs():
+    from qcs_b200 import build
+    return build.build_all()
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qcs?_[a-z0-9_]+)\s*\(", text)))
+
+
+def _exported(path):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", path], text=True)
+    return {line.split()[-1] for line in out.splitlines() if " T " in line}
+
+
+def test_cuda_abi_exports_every_declared_symbol(libs):
+    declared = [s for s in _declared("qcs_cuda.h") if s.startswith("qcs_cuda_")]
+    assert len(declared) >= 25
+    missing = [s for s in declared if s not in _exported(libs["cuda"])]
+    assert not missing, missing
+
+
+def test_host_api_exports_every_declared_symbol(libs):
+    declared = _declared("qcs.h")
+    assert len(declared) == 30, declared   # the reference's 28 + qc_cphase + qc_add_gate
+    missing = [s for s in declared if s not in _exported(libs["host"])]
+    assert not missing, missing
+    assert "qc_cuda_engine" in _exported(libs["host"])
+
+
+def test_header_matches_reference_prototypes(libs):
+    """Same function names as the reference header."""
+    ref = ["qc_create", "qc_destroy", "qc_h", "qc_x", "qc_y", "qc_z", "qc_cnot", "qc_phase",
+           "qc_rx", "qc_ry", "qc_rz", "qc_barrier", "qc_reset", "qc_measure", "qc_measure_all",
+           "qc_run", "qc_run_shots", "qc_find_most_likely_state", "qc_get_probability",
+           "qc_print_state", "qc_print_circuit", "qc_grover_search",
+           "qc_quantum_fourier_transform", "qc_bernstein_vazirani", "qc_ghz_state",
+           "qc_get_num_qubits", "qc_get_num_gates", "qc_optimize"]
+    assert len(ref) == 28
+    declared = _declared("qcs.h")
+    for name in ref:
+        assert name in declared, name
+
+
+def test_bindings_cover_the_abi(libs):
+    from qcs_b200 import _ffi
+    declared = [s for s in _declared("qcs_cuda.h") if s.startswith("qcs_cuda_")]
+    assert sorted(_ffi.CUDA_ABI) == sorted(declared)
+    _ffi.load()
+
+
+def test_no_cpu_fallback_without_device(libs):
+    """On a box without a GPU qc_create must fail loudly (NULL + message), never compute on the CPU."""
+    if os.path.exists("/dev/nvidiactl") or os.path.exists("/dev/nvidia0"):
+        pytest.skip("a GPU is present")
+    from qcs_b200 import Circuit, QcsError
+    with pytest.raises(QcsError):
+        Circuit(3)
+
+
+def _history_script():
+    return [("h", 0), ("h", 0), ("x", 1), ("cnot", 0, 1), ("cnot", 0, 1), ("y", 2), ("y", 2),
+            ("rz", 1, 0.5), ("z", 1), ("z", 1), ("barrier",), ("h", 9), ("cnot", 1, 1),
+            ("cphase", 0, 2, 0.3), ("x", 2), ("x", 2), ("phase", 0, 1.0)]
+
+
+def test_history_and_optimize_match_reference(libs):
+    if not po.ref_available("seq"):
+        pytest.skip("oracle/_ref not built")
+    from qcs_b200 import Circuit
+    ref = po.RefLib(3, "seq")
+    c = Circuit(3, dryrun=True)
+    po.replay(ref, _history_script()); po.replay(c, _history_script())
+    assert c.num_gates == ref.num_gates == len(_history_script())
+    ref.optimize(); c.optimize()
+    assert c.num_gates == ref.num_gates
+    # H,H / CNOT,CNOT / Y,Y / Z,Z / X,X cancel; cascades rescan from the start
+    assert c.num_gates == len(_history_script()) - 10
+
+
+def _capture_stdout(fn):
+    import tempfile
+    libc = ctypes.CDLL(None)
+    libc.fflush(None)
+    saved = os.dup(1)
+    with tempfile.TemporaryFile() as tmp:
+        os.dup2(tmp.fileno(), 1)
+        try:
+            fn()
+            libc.fflush(None)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        tmp.seek(0)
+        return tmp.read()
+
+
+def test_print_circuit_is_byte_identical(libs):
+    if not po.ref_available("seq"):
+        pytest.skip("oracle/_ref not built")
+    from qcs_b200 import Circuit
+    script = [("h", 0), ("x", 1), ("cnot", 0, 2), ("rz", 1, 0.2), ("cnot", 2, 1), ("barrier",), ("y", 0)]
+    ref = po.RefLib(3, "seq"); c = Circuit(3, dryrun=True)
+    po.replay(ref, script); po.replay(c, script)
+    ref.L.qc_print_circuit.argtypes = [ctypes.c_void_p]
+    want = _capture_stdout(lambda: ref.L.qc_print_circuit(ref.c))
+    got = _capture_stdout(lambda: c.print_circuit())
+    assert got == want and b"QUANTUM CIRCUIT" in got
+
+
+def test_invalid_gates_are_recorded_but_not_queued(libs):
+    """Reference quirk D13: a rejected gate still lands in the history (src/qcs.c:161-163)."""
+    from qcs_b200 import Circuit
+    c = Circuit(3, dryrun=True)
+    c.h(7); c.cnot(1, 1); c.x(-1); c.h(0)
+    assert c.num_gates == 4
+    c.flush()
+    assert c.stats()["gates_submitted"] == 1

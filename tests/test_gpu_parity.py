@@ -1,0 +1,258 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the CPU oracle and
+the golden vectors of the real reference.
+
+Bar (north star): gate arithmetic bit-exact (== on every double); measurement
+outcomes, shot histograms and argmax exact; Grover (whose diffusion sums the
+amplitudes in a different order on the device) within 1e-12 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.golden.cases import CASES
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz")
+REL_TOL = 1e-12  # north star: "within 1e-12 relative (fp64)"
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+def Circuit(*a, **k):
+    from qcs_b200 import Circuit as C
+    return C(*a, **k)
+
+
+def _same(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    return a.shape == b.shape and bool(np.all(a == b))
+
+
+def _close(a, b, tol=REL_TOL):
+    a = np.asarray(a); b = np.asarray(b)
+    scale = max(np.max(np.abs(b)), 1e-300)
+    return a.shape == b.shape and bool(np.all(np.abs(a - b) <= tol * scale))
+
+
+def _uses_grover(script):
+    return any(op[0] == "grover" for op in script)
+
+
+@pytest.mark.parametrize("fusion", ["on", "off"])
+@pytest.mark.parametrize("sem", ["reference", "corrected"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_cases(golden, name, sem, fusion):
+    n, script = CASES[name]
+    c = Circuit(n, semantics=sem, fusion=fusion)
+    vals = po.replay(c, script)
+    key = f"{name}/{sem}"
+    exact = not _uses_grover(script)
+    cmp = _same if exact else _close
+    assert cmp(c.state(), golden[key + "/state"]), "live amplitudes differ"
+    if sem == "reference":
+        assert cmp(c.scratch(), golden[key + "/scratch"]), "scratch amplitudes differ"
+    for k, (kind, v) in enumerate(vals):
+        want = golden[f"{key}/out{k}_{kind}"]
+        if kind == "prob" and not exact:
+            assert _close(v, want), f"output {k} ({kind})"
+        else:
+            assert _same(v, want), f"output {k} ({kind}) differs: {v} vs {want}"
+    c.close()
+
+
+def _random_script(rng, n, length, generic=True):
+    s = []
+    for _ in range(length):
+        k = int(rng.integers(0, 12 if generic else 10))
+        q = int(rng.integers(0, n))
+        c = int(rng.integers(0, n - 1)); c = c if c < q else c + 1
+        ang = float(rng.uniform(-3, 3))
+        s.append([("h", q), ("x", q), ("y", q), ("z", q), ("phase", q, ang), ("rx", q, ang),
+                  ("ry", q, ang), ("rz", q, ang), ("cnot", c, q), ("cphase", c, q, ang),
+                  ("apply_1q", list(rng.normal(size=8)), q),
+                  ("apply_c1q", list(rng.normal(size=8)), c, q)][k])
+    return s
+
+
+@pytest.mark.parametrize("tile_kernel", ["tma", "tma16", "ldg"])
+@pytest.mark.parametrize("sem", ["reference", "corrected"])
+@pytest.mark.parametrize("n", [12, 13, 15, 17, 21])
+def test_fused_random_circuits_bit_exact(n, sem, tile_kernel):
+    """Fused tile passes (n >= 12) vs oracle: every amplitude equal, random start state."""
+    rng = np.random.default_rng(1000 + n)
+    for trial in range(4 if n < 20 else 1):
+        script = _random_script(rng, n, 60 + 40 * trial)
+        init = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+        orc = po.Oracle(n, sem); c = Circuit(n, semantics=sem, tile_kernel=tile_kernel)
+        orc.load_state(init); c.load_state(init)
+        po.replay(orc, script); po.replay(c, script)
+        got, want = c.state(), orc.state()
+        assert _same(got, want), f"n={n} trial={trial}: {np.sum(got != want)} amplitudes differ\n{c.describe_plan()[:2000]}"
+        if sem == "reference":
+            assert _same(c.scratch(), orc.scratch())
+        st = c.stats()
+        assert st["passes"] > 0 and st["passes"] < len(script), st
+        orc.close(); c.close()
+
+
+@pytest.mark.parametrize("tile_kernel", ["tma", "tma16", "ldg"])
+@pytest.mark.parametrize("sem", ["reference", "corrected"])
+def test_every_target_control_pair(sem, tile_kernel):
+    """Each (control, target) placement -- lane, warp, register, outside-tile bits -- for each gate class."""
+    n = 14
+    rng = np.random.default_rng(7)
+    init = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    mats = {
+        "generic": list(rng.normal(size=8)),
+        "real": [0.3, 0, -0.8, 0, 1.1, 0, 0.4, 0],
+        "hsym": [0.6, 0, 0.7, 0, 0.6, 0, -0.7, 0],
+        "swap": [0, 0, 1, 0, 1, 0, 0, 0],
+        "diag": [0.5, -0.2, 0, 0, 0, 0, -0.3, 0.9],
+        "phase": [1, 0, 0, 0, 0, 0, 0.28, 0.96],
+    }
+    for cls, m in mats.items():
+        orc = po.Oracle(n, sem); c = Circuit(n, semantics=sem, tile_kernel=tile_kernel)
+        orc.load_state(init); c.load_state(init)
+        for t in range(n):
+            orc.apply_1q(m, t); c.apply_1q(m, t)
+            for ctl in range(n):
+                if ctl != t and (ctl + t) % 3 == 0:
+                    orc.apply_c1q(m, ctl, t); c.apply_c1q(m, ctl, t)
+        assert _same(c.state(), orc.state()), cls
+        orc.close(); c.close()
+
+
+@pytest.mark.parametrize("sem", ["reference", "corrected"])
+def test_drivers_vs_oracle(sem):
+    for n in (12, 14, 18):
+        for drv, arg in (("qft", None), ("ghz", None), ("bv", 0x2A5 & ((1 << (n - 1)) - 1))):
+            orc = po.Oracle(n, sem); c = Circuit(n, semantics=sem)
+            for b in (orc, c):
+                b.x(1); b.ry(n - 1, 0.37); b.h(5)
+                getattr(b, drv)(*([] if arg is None else [arg]))
+            assert _same(c.state(), orc.state()), (n, drv)
+            assert c.find_most_likely_state() == orc.find_most_likely_state()
+            orc.close(); c.close()
+
+
+@pytest.mark.parametrize("sem", ["reference", "corrected"])
+@pytest.mark.parametrize("n", [4, 10, 14])
+def test_grover_within_tolerance(n, sem):
+    sol = 0xABCDE % (1 << n)
+    orc = po.Oracle(n, sem); c = Circuit(n, semantics=sem)
+    orc.grover_search(sol); c.grover_search(sol)
+    assert _close(c.state(), orc.state())
+    assert abs(c.get_probability(sol) - orc.get_probability(sol)) <= REL_TOL * max(1.0, orc.get_probability(sol))
+    assert c.find_most_likely_state() == orc.find_most_likely_state()
+    assert c.num_gates == n + 2 * po.Oracle.lib().orc_grover_iterations(n)
+    orc.close(); c.close()
+
+
+@pytest.mark.parametrize("n", [3, 9, 10, 11, 13, 16, 20])
+def test_exact_sequential_sums(n):
+    """prob_0 and the normalisation total are the reference's left-to-right rounded sums, bit for bit."""
+    rng = np.random.default_rng(50 + n)
+    for kind in ("dense", "sparse", "uniform", "skewed"):
+        if kind == "dense":
+            init = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+        elif kind == "sparse":
+            init = np.zeros(2 ** n, complex)
+            idx = rng.integers(0, 2 ** n, size=5)
+            init[idx] = rng.normal(size=5) + 1j * rng.normal(size=5)
+        elif kind == "uniform":
+            init = np.full(2 ** n, 2.0 ** (-n / 2), complex)
+        else:
+            init = (rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)) * np.exp(rng.uniform(-30, 3, size=2 ** n))
+        init = init / np.linalg.norm(init)
+        orc = po.Oracle(n, "corrected"); c = Circuit(n, semantics="corrected")
+        orc.load_state(init); c.load_state(init)
+        for q in sorted({0, 1, n // 2, n - 1}):
+            want = po.Oracle.lib().orc_prob0(orc.h_, q)
+            assert c.prob0(q) == want, (kind, q, c.prob0(q), want)
+        orc.normalize(); c.normalize()
+        assert _same(c.state(), orc.state()), kind
+        orc.close(); c.close()
+
+
+@pytest.mark.parametrize("n,shots", [(2, 500), (9, 2000), (12, 4000), (16, 3000)])
+def test_shots_and_measurement_exact(n, shots):
+    rng = np.random.default_rng(90 + n)
+    script = _random_script(rng, n, 30, generic=False)
+    for sem in ("reference", "corrected"):
+        orc = po.Oracle(n, sem); c = Circuit(n, semantics=sem)
+        po.replay(orc, script); po.replay(c, script)
+        if sem == "reference":  # as-written controlled gates leave the state unnormalised
+            orc.normalize(); c.normalize()
+        po.srand(4242); want_sh = orc.run_shots(shots); want_m = orc.measure_all()
+        po.srand(4242); got_sh = c.run_shots(shots); got_m = c.measure_all()
+        assert _same(got_sh, want_sh)
+        assert got_m == want_m
+        assert _same(c.state(), orc.state())
+        orc.close(); c.close()
+
+
+def test_dropped_shots_like_reference():
+    """Norm < 1 (as-written GHZ): shots with u >= total are silently dropped (KAT-3)."""
+    po.srand(7)
+    c = Circuit(2, semantics="reference"); c.h(0); c.cnot(0, 1)
+    assert list(c.run_shots(1000)) == [484, 0, 0, 0]
+    c.close()
+
+
+def test_fusion_on_off_identical_large():
+    """26 qubits (1 GiB): fused passes vs one kernel per gate, every amplitude equal."""
+    n = 26
+    script = po.random_circuit_script(n, 3, seed=99) + [("qft",)]
+    out = []
+    for fusion in ("on", "off"):
+        c = Circuit(n, semantics="corrected", fusion=fusion)
+        po.replay(c, script)
+        out.append(c.state())
+        if fusion == "on":
+            st = c.stats()
+            assert st["passes"] * 4 < st["gates_executed"], st
+        c.close()
+    assert _same(out[0], out[1])
+    assert abs(np.sum(np.abs(out[0]) ** 2) - 1.0) < 1e-10
+
+
+def test_qft30_roundtrip_and_uniform():
+    """BASELINE config 3 at full size: QFT of |0..0> is exactly uniform; QFT then inverse QFT returns the input."""
+    import math
+    n = 30
+    c = Circuit(n, semantics="corrected")
+    c.qft()
+    h = 1.0 / math.sqrt(2.0)
+    a = 1.0
+    for _ in range(n):
+        a = h * a  # the value repeated Hadamards produce, rounded like the reference
+    H, C = c.H, c.C
+    import ctypes
+    for idx in (0, 1, 12345, 2 ** 29 + 7, 2 ** 30 - 1):
+        out = (ctypes.c_double * 2)()
+        assert C.qcs_cuda_get_amplitude(c.e, idx, out) == 0
+        assert out[0] == a and out[1] == 0.0, (idx, out[0], a)
+    st = c.stats()
+    assert st["gates_submitted"] == n * (n + 1) // 2
+    assert st["passes"] <= 40, st
+    c.close()
+    # round trip on a non-trivial basis state
+    c = Circuit(n, semantics="corrected")
+    x = 0x2F0F3A71 & ((1 << n) - 1)
+    for q in range(n):
+        if (x >> q) & 1:
+            c.x(q)
+    c.qft()
+    for i in reversed(range(n)):          # inverse: reversed order, negated angles
+        for j in reversed(range(i + 1, n)):
+            c.cphase(j, i, -math.pi / float(1 << (j - i)))
+        c.h(i)
+    assert abs(c.get_probability(x) - 1.0) < 1e-12
+    assert c.find_most_likely_state() == x
+    c.close()
