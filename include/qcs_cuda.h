@@ -100,7 +100,7 @@ int qcs_cuda_write_amplitudes(qcs_cuda_engine *e, int which, long first,
 
 /* ---- configuration / introspection ------------------------------------------------ */
 /* Keys: "semantics" = reference|corrected, "fusion" = on|off,
- * "dryrun" = 0|1, "pass_flops" = <int>, "tile_kernel" = ldg|tma.
+ * "dryrun" = 0|1, "pass_flops" = <float>, "tile_kernel" = ldg|tma|tma16.
  * Defaults come from QCS_CUDA_<KEY> in the environment; set_default applies
  * to engines created afterwards. */
 int qcs_cuda_set_default(const char *key, const char *value);
@@ -125,6 +125,12 @@ int qcs_cuda_reset_stats(qcs_cuda_engine *e);
 /* When enabled (non-zero) every fused pass is bracketed by CUDA events on the
  * engine's stream so pass_ms is filled in (used by bench.py's roofline). */
 int qcs_cuda_set_timing(qcs_cuda_engine *e, int enabled);
+
+/* Device-side stopwatch: record a CUDA event on the engine's stream (slot 0..7),
+ * later read the elapsed device time between two recorded slots (synchronises). */
+int qcs_cuda_marker_record(qcs_cuda_engine *e, int slot);
+int qcs_cuda_marker_elapsed_ms(qcs_cuda_engine *e, int from_slot, int to_slot,
+                               double *ms);
 
 /* Writes a human-readable description of the passes the last flush executed
  * (tile bits, segments, gates per segment) into buf; returns bytes needed. */

@@ -58,6 +58,8 @@ CUDA_ABI = {
     "qcs_cuda_get_stats": (_I, [_P, ctypes.POINTER(Stats)]),
     "qcs_cuda_reset_stats": (_I, [_P]),
     "qcs_cuda_set_timing": (_I, [_P, _I]),
+    "qcs_cuda_marker_record": (_I, [_P, _I]),
+    "qcs_cuda_marker_elapsed_ms": (_I, [_P, _I, _I, _DP]),
     "qcs_cuda_describe_last_plan": (_L, [_P, ctypes.c_char_p, _L]),
     "qcs_cuda_last_error": (ctypes.c_char_p, []),
     "qcs_cuda_dist_unique_id": (_I, [ctypes.c_char_p]),

@@ -177,6 +177,13 @@ class Circuit:
             idx.ctypes.data_as(ctypes.POINTER(ctypes.c_long))))
         return idx
 
+    def marker(self, slot: int): self._ck(self.C.qcs_cuda_marker_record(self.e, slot))
+
+    def marker_elapsed_ms(self, a: int, b: int) -> float:
+        ms = ctypes.c_double()
+        self._ck(self.C.qcs_cuda_marker_elapsed_ms(self.e, a, b, ctypes.byref(ms)))
+        return ms.value
+
     def set_timing(self, enabled: bool): self._ck(self.C.qcs_cuda_set_timing(self.e, int(enabled)))
 
     def stats(self) -> dict:

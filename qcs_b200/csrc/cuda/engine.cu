@@ -76,7 +76,8 @@ static int load_options(Options &o) {
   v = option_value("tile_kernel");
   if (v == "ldg") o.tile_kernel = 0;
   else if (v == "tma16") o.tile_kernel = 1;
-  else if (v.empty() || v == "tma" || v == "tma8") o.tile_kernel = 2;
+  else if (v == "tma" || v == "tma8") o.tile_kernel = 2;
+  else if (v.empty()) o.tile_kernel = Options().tile_kernel;
   else return set_error(QCS_CUDA_ERR_INVALID, "tile_kernel must be ldg|tma|tma16, got '%s'", v.c_str());
   v = option_value("exchange");
   o.exchange = (v == "p2p") ? 1 : 0;
@@ -491,6 +492,7 @@ void qcs_cuda_state_destroy(qcs_cuda_engine *e) {
   for (auto &pr : e->pending_pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto &pr : e->pending_xchg_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);
+  for (auto ev : e->markers) if (ev) cudaEventDestroy(ev);
   cudaFree(e->live);
   cudaFree(e->scratch);
   cudaFree(e->staging);
@@ -783,6 +785,25 @@ int qcs_cuda_reset_stats(qcs_cuda_engine *e) {
   fold_events(*e);
   e->gates_submitted = e->gates_executed = e->passes = e->kernel_launches = e->segments = e->remaps = 0;
   e->algorithmic_bytes = e->pass_bytes = e->pass_ms = e->exchange_bytes = e->exchange_ms = 0;
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_marker_record(qcs_cuda_engine *e, int slot) {
+  if (!e || slot < 0 || slot >= 8) return set_error(QCS_CUDA_ERR_INVALID, "bad marker slot");
+  RC(require_data(*e));
+  if (!e->markers[slot]) CK(cudaEventCreate(&e->markers[slot]));
+  CK(cudaEventRecord(e->markers[slot], e->stream));
+  return QCS_CUDA_OK;
+}
+
+int qcs_cuda_marker_elapsed_ms(qcs_cuda_engine *e, int from_slot, int to_slot, double *ms) {
+  if (!e || !ms || from_slot < 0 || from_slot >= 8 || to_slot < 0 || to_slot >= 8 ||
+      !e->markers[from_slot] || !e->markers[to_slot])
+    return set_error(QCS_CUDA_ERR_INVALID, "marker not recorded");
+  CK(cudaEventSynchronize(e->markers[to_slot]));
+  float f = 0.f;
+  CK(cudaEventElapsedTime(&f, e->markers[from_slot], e->markers[to_slot]));
+  *ms = (double)f;
   return QCS_CUDA_OK;
 }
 

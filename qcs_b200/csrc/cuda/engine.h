@@ -19,7 +19,7 @@ struct Options {
   bool dryrun = false;
   double pass_flops = 96.0;
   int exchange = 0;  // 0: NCCL send/recv, 1: peer-memory swap kernel
-  int tile_kernel = 2;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8)
+  int tile_kernel = 0;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8)
 };
 
 struct DistContext {
@@ -64,6 +64,7 @@ struct Engine {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_pass_events;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_xchg_events;
   std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t markers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // engine.cu
