@@ -105,6 +105,9 @@ int qcs_cuda_write_amplitudes(qcs_cuda_engine *e, int which, long first,
  * to engines created afterwards. */
 int qcs_cuda_set_default(const char *key, const char *value);
 int qcs_cuda_num_qubits(const qcs_cuda_engine *e);
+/* Current layout: perm[q] = physical index position of logical qubit q (identity on one GPU;
+ * position swaps change it when the state is sharded).  perm must hold n_qubits ints. */
+int qcs_cuda_get_layout(const qcs_cuda_engine *e, int *perm);
 
 typedef struct qcs_cuda_stats {
   long gates_submitted;     /* qcs_cuda_apply_* calls accepted            */
@@ -136,6 +139,14 @@ int qcs_cuda_marker_elapsed_ms(qcs_cuda_engine *e, int from_slot, int to_slot,
  * (tile bits, segments, gates per segment) into buf; returns bytes needed. */
 long qcs_cuda_describe_last_plan(qcs_cuda_engine *e, char *buf, long cap);
 
+/* Dry-run engines record what a real engine would execute, in order.  Entry i is
+ * written as 12 doubles: out[0] = 1 (gate) or 2 (position swap);
+ *   gate: out[1] = kind | flags << 8 (common.h GateKind / GateFlags), out[2] = target position,
+ *         out[3] = control position (-1: none), out[4..12) = the 2x2 matrix;
+ *   swap: out[1] = local position, out[2] = global position;  out[0] = 3: both positions local.
+ * Returns the number of entries; fills `out` when index is in range. */
+long qcs_cuda_trace_read(qcs_cuda_engine *e, long index, double out[12]);
+
 const char *qcs_cuda_last_error(void);
 
 /* ---- multi-GPU (one process per GPU; NCCL over NVLink) ---------------------------- */
@@ -145,6 +156,11 @@ const char *qcs_cuda_last_error(void);
 int qcs_cuda_dist_unique_id(char id[128]);
 int qcs_cuda_dist_init(int rank, int world, const char id[128], int device);
 int qcs_cuda_dist_finalize(void);
+/* Plan-only sharding (no NCCL, no GPU): engines created afterwards must be
+ * dry-run ("dryrun" = 1); they plan passes and position swaps exactly as rank
+ * `rank` of `world` would and record them in the trace below.  Used by the CPU
+ * tests that replay the schedule with two gloo processes. */
+int qcs_cuda_dist_init_plan_only(int rank, int world);
 int qcs_cuda_dist_rank(void);
 int qcs_cuda_dist_world(void);
 

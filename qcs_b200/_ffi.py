@@ -55,6 +55,7 @@ CUDA_ABI = {
     "qcs_cuda_write_amplitudes": (_I, [_P, _I, _L, _L, _DP]),
     "qcs_cuda_set_default": (_I, [ctypes.c_char_p, ctypes.c_char_p]),
     "qcs_cuda_num_qubits": (_I, [_P]),
+    "qcs_cuda_get_layout": (_I, [_P, _IP]),
     "qcs_cuda_get_stats": (_I, [_P, ctypes.POINTER(Stats)]),
     "qcs_cuda_reset_stats": (_I, [_P]),
     "qcs_cuda_set_timing": (_I, [_P, _I]),
@@ -65,6 +66,8 @@ CUDA_ABI = {
     "qcs_cuda_dist_unique_id": (_I, [ctypes.c_char_p]),
     "qcs_cuda_dist_init": (_I, [_I, _I, ctypes.c_char_p, _I]),
     "qcs_cuda_dist_finalize": (_I, []),
+    "qcs_cuda_dist_init_plan_only": (_I, [_I, _I]),
+    "qcs_cuda_trace_read": (_L, [_P, _L, _DP]),
     "qcs_cuda_dist_rank": (_I, []),
     "qcs_cuda_dist_world": (_I, []),
 }

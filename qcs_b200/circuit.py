@@ -193,6 +193,28 @@ class Circuit:
 
     def reset_stats(self): self._ck(self.C.qcs_cuda_reset_stats(self.e))
 
+    def layout(self) -> list:
+        """perm[q] = physical index position of logical qubit q."""
+        perm = (ctypes.c_int * self.n)()
+        self._ck(self.C.qcs_cuda_get_layout(self.e, perm))
+        return list(perm)
+
+    def trace(self) -> list:
+        """Dry-run engines: the ordered list of physical gates / position swaps a real engine would run."""
+        out = []
+        buf = (ctypes.c_double * 12)()
+        n = self.C.qcs_cuda_trace_read(self.e, -1, buf)
+        for i in range(n):
+            self.C.qcs_cuda_trace_read(self.e, i, buf)
+            if buf[0] == 2.0:
+                out.append(("swap", int(buf[1]), int(buf[2])))
+            elif buf[0] == 3.0:
+                out.append(("swap_local", int(buf[1]), int(buf[2])))
+            else:
+                kf = int(buf[1])
+                out.append(("gate", kf & 0xff, kf >> 8, int(buf[2]), int(buf[3]), [buf[4 + k] for k in range(8)]))
+        return out
+
     def describe_plan(self) -> str:
         need = self.C.qcs_cuda_describe_last_plan(self.e, None, 0)
         buf = ctypes.create_string_buffer(int(need) + 1)

@@ -247,6 +247,19 @@ int qcs_cuda_dist_init(int rank, int world, const char id[128], int device) {
   return QCS_CUDA_OK;
 }
 
+int qcs_cuda_dist_init_plan_only(int rank, int world) {
+  DistContext &d = dist();
+  if (d.active) return set_error(QCS_CUDA_ERR_INVALID, "communicator already initialised");
+  if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world)
+    return set_error(QCS_CUDA_ERR_INVALID, "world size must be a power of two (got %d)", world);
+  d = DistContext();
+  d.rank = rank;
+  d.world = world;
+  while ((1 << d.rank_bits) < world) d.rank_bits++;
+  d.active = world > 1;
+  return QCS_CUDA_OK;
+}
+
 int qcs_cuda_dist_finalize(void) {
   DistContext &d = dist();
   if (d.comm) ncclCommDestroy((ncclComm_t)d.comm);

@@ -156,6 +156,17 @@ static double gate_bytes(const Engine &e, const PhysGate &g) {
 // Runs a list of physical gates whose pairing targets are all local.
 static int run_local(Engine &e, const std::vector<PhysGate> &gates, bool record_plan) {
   if (gates.empty()) return QCS_CUDA_OK;
+  if (e.opt.dryrun) {
+    for (const PhysGate &g : gates) {
+      Engine::TraceEntry t{};
+      t.v[0] = 1.0;
+      t.v[1] = (double)(g.c.kind | (g.c.flags << 8));
+      t.v[2] = (double)g.tpos;
+      t.v[3] = (double)g.cpos;
+      for (int k = 0; k < 8; k++) t.v[4 + k] = g.c.m[k];
+      e.trace.push_back(t);
+    }
+  }
   const bool fused = e.opt.fusion && e.nl >= QCS_TILE_BITS;
   if (fused) {
     PlannerConfig cfg;
@@ -239,6 +250,13 @@ static int pick_victim(const Engine &e, const std::vector<HostGate> &q, size_t f
 
 static int swap_positions(Engine &e, int lpos, int gpos) {
   if (!e.opt.dryrun) RC(dist_swap_positions(e, lpos, gpos));
+  else {
+    Engine::TraceEntry t{};
+    t.v[0] = 2.0;
+    t.v[1] = (double)lpos;
+    t.v[2] = (double)gpos;
+    e.trace.push_back(t);
+  }
   const int ql = e.inv_perm[lpos], qg = e.inv_perm[gpos];
   e.perm[ql] = gpos;
   e.perm[qg] = lpos;
@@ -290,12 +308,34 @@ static int flush(Engine &e) {
   return QCS_CUDA_OK;
 }
 
+// Trades two LOCAL positions (a bit permutation of the shard, no communication).
+static int swap_local_positions(Engine &e, int a, int b) {
+  if (a == b) return QCS_CUDA_OK;
+  if (!e.opt.dryrun) {
+    CK(launch_swap_local_bits(e.live, e.nl, a, b, e.stream));
+    e.kernel_launches++;
+    e.algorithmic_bytes += 16.0 * (double)e.local_size;
+  } else {
+    Engine::TraceEntry t{};
+    t.v[0] = 3.0;
+    t.v[1] = (double)a;
+    t.v[2] = (double)b;
+    e.trace.push_back(t);
+  }
+  const int qa = e.inv_perm[a], qb = e.inv_perm[b];
+  e.perm[qa] = b;
+  e.perm[qb] = a;
+  e.inv_perm[a] = qb;
+  e.inv_perm[b] = qa;
+  return QCS_CUDA_OK;
+}
+
 // Restores the identity qubit layout (needed by every order-dependent read).
 static int canonicalize(Engine &e) {
+  // 1. bring every global qubit home (half-shard exchanges)
   for (int g = e.nl; g < e.n; g++) {
     while (e.inv_perm[g] != g) {
-      // logical qubit g currently sits at local position perm[g] (or another global one)
-      const int where = e.perm[g];
+      const int where = e.perm[g];  // position currently holding logical qubit g
       if (where < e.nl) {
         RC(swap_positions(e, where, g));
       } else {
@@ -304,8 +344,11 @@ static int canonicalize(Engine &e) {
       }
     }
   }
-  // local-local permutations never arise: swaps only trade a local for a global position,
-  // and restoring every global position restores the locals too.
+  // 2. successive swaps through one global position leave the local qubits permuted among
+  //    themselves: undo with local bit swaps
+  for (int p = 0; p < e.nl; p++) {
+    while (e.inv_perm[p] != p) RC(swap_local_positions(e, p, e.inv_perm[p]));
+  }
   for (int q = 0; q < e.n; q++)
     if (e.perm[q] != q) return set_error(QCS_CUDA_ERR_CUDA, "internal: layout not canonical");
   return QCS_CUDA_OK;
@@ -439,6 +482,10 @@ int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
     *out = e;
     return QCS_CUDA_OK;
   }
+  if (d.active && !d.comm) {
+    delete e;
+    return set_error(QCS_CUDA_ERR_INVALID, "plan-only sharding needs dry-run engines");
+  }
   auto fail = [&](int code) {
     qcs_cuda_state_destroy(e);
     return code;
@@ -512,6 +559,12 @@ void qcs_cuda_state_destroy(qcs_cuda_engine *e) {
 }
 
 int qcs_cuda_num_qubits(const qcs_cuda_engine *e) { return e ? e->n : 0; }
+
+int qcs_cuda_get_layout(const qcs_cuda_engine *e, int *perm) {
+  if (!e || !perm) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  for (int q = 0; q < e->n; q++) perm[q] = e->perm[q];
+  return QCS_CUDA_OK;
+}
 
 int qcs_cuda_apply_1q(qcs_cuda_engine *e, const double m[8], int target) {
   if (!e || !m) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
@@ -805,6 +858,13 @@ int qcs_cuda_marker_elapsed_ms(qcs_cuda_engine *e, int from_slot, int to_slot, d
   CK(cudaEventElapsedTime(&f, e->markers[from_slot], e->markers[to_slot]));
   *ms = (double)f;
   return QCS_CUDA_OK;
+}
+
+long qcs_cuda_trace_read(qcs_cuda_engine *e, long index, double out[12]) {
+  if (!e) return 0;
+  if (out && index >= 0 && (size_t)index < e->trace.size())
+    std::memcpy(out, e->trace[(size_t)index].v, sizeof(double) * 12);
+  return (long)e->trace.size();
 }
 
 long qcs_cuda_describe_last_plan(qcs_cuda_engine *e, char *buf, long cap) {

@@ -55,6 +55,8 @@ struct Engine {
 
   std::vector<HostGate> queue;
   std::vector<PassPlan> last_plan;
+  struct TraceEntry { double v[12]; };
+  std::vector<TraceEntry> trace;  // dry-run only
 
   // statistics
   long long gates_submitted = 0, gates_executed = 0, passes = 0, kernel_launches = 0,

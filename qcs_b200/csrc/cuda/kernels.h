@@ -17,6 +17,8 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
 cudaError_t launch_simple_gate(double2 *state, const DGate &g, int n_local,
                                uint64_t shard_base, cudaStream_t stream);
 
+cudaError_t launch_swap_local_bits(double2 *state, int n_local, int a, int b, cudaStream_t stream);
+
 // kernels_reduce.cu -----------------------------------------------------------
 struct ReduceWorkspace {
   double *partials;        // device, >= 4 * REDUCE_MAX_BLOCKS doubles

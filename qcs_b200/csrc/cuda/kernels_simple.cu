@@ -61,7 +61,33 @@ simple_diag_kernel(double2 *__restrict__ state, const __grid_constant__ DGate g,
   }
 }
 
+// Swaps two LOCAL index bits a < b of the whole shard in place: amplitude (..a=1,b=0..) trades
+// places with (..a=0,b=1..).  Used to restore the identity qubit layout after position swaps.
+__global__ void __launch_bounds__(256)
+swap_local_bits_kernel(double2 *__restrict__ state, int a, int b, uint64_t n_items) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < n_items;
+       item += stride) {
+    const uint64_t base = insert_zero(insert_zero(item, a), b);
+    const uint64_t i = base | (1ull << a);
+    const uint64_t j = base | (1ull << b);
+    const double2 vi = state[i];
+    const double2 vj = state[j];
+    state[i] = vj;
+    state[j] = vi;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_swap_local_bits(double2 *state, int n_local, int a, int b, cudaStream_t stream) {
+  if (a == b) return cudaSuccess;
+  if (a > b) { int t = a; a = b; b = t; }
+  const uint64_t n_items = (1ull << n_local) >> 2;
+  const unsigned blocks = (unsigned)((n_items + 255) / 256 > 148 * 16 ? 148 * 16 : (n_items + 255) / 256);
+  swap_local_bits_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(state, a, b, n_items ? n_items : 1);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_simple_gate(double2 *state, const DGate &g, int n_local, uint64_t shard_base,
                                cudaStream_t stream) {

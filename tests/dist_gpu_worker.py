@@ -1,0 +1,86 @@
+"""Multi-GPU parity worker (one process per GPU, NCCL): run under torchrun by
+tests/test_dist_gpu.py or by hand:
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/dist_gpu_worker.py
+Every rank drives the same circuit through the public C API on a sharded engine and compares
+its shard (and every global read) with the CPU oracle run on the unsharded state."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    from qcs_b200 import Circuit, _ffi
+    _, C = _ffi.load()
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        assert C.qcs_cuda_dist_unique_id(buf) == 0, _ffi.last_error()
+        uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    assert C.qcs_cuda_dist_init(rank, world, bytes(uid.cpu().numpy().tobytes()), lr) == 0, _ffi.last_error()
+    from tests.test_dist_gloo import CASES
+    ok = True
+
+    def check(cond, msg):
+        nonlocal ok
+        if not cond:
+            ok = False
+            print(f"[rank {rank}] FAIL {msg}", flush=True)
+
+    for fusion in ("on", "off"):
+        for name, (n, sem, script) in CASES.items():
+            c = Circuit(n, semantics=sem, fusion=fusion)
+            orc = po.Oracle(n, sem)
+            po.replay(c, script); po.replay(orc, script)
+            c.flush(); st = c.stats()
+            first, count = c._shard()
+            got = c.state(); want = orc.state()[first:first + count]
+            check(np.all(got == want), f"{name}/{fusion}: {int(np.sum(got != want))} shard amplitudes differ")
+            check(c.find_most_likely_state() == orc.find_most_likely_state(), f"{name}: argmax")
+            for idx in (0, 5, (1 << n) - 1, (1 << (n - 1)) + 3):
+                check(c.get_probability(idx) == orc.get_probability(idx), f"{name}: prob {idx}")
+            if sem == "reference":
+                orc.normalize(); c.normalize()
+            for q in (0, n - 1, n - 2):
+                check(c.prob0(q) == po.Oracle.lib().orc_prob0(orc.h_, q), f"{name}: prob0({q})")
+            po.srand(99); want_sh = orc.run_shots(3000); want_m = [orc.measure(n - 1), orc.measure(0), orc.measure(n - 2)]
+            po.srand(99); got_sh = c.run_shots(3000); got_m = [c.measure(n - 1), c.measure(0), c.measure(n - 2)]
+            check(np.array_equal(got_sh, want_sh), f"{name}: shots")
+            check(got_m == want_m, f"{name}: measure {got_m} vs {want_m}")
+            got = c.state(); want = orc.state()[first:first + count]
+            check(np.all(got == want), f"{name}/{fusion}: post-measurement shard differs")
+            if rank == 0:
+                print(f"done {name}/{fusion}: passes={st['passes']} remaps={st['remaps']}", flush=True)
+            c.close(); orc.close()
+    # Grover across ranks (allreduced diffusion mean): tolerance 1e-12
+    for sem in ("corrected", "reference"):
+        n = 13
+        c = Circuit(n, semantics=sem); orc = po.Oracle(n, sem)
+        c.grover_search(5000); orc.grover_search(5000)
+        first, count = c._shard()
+        got = c.state(); want = orc.state()[first:first + count]
+        scale = np.max(np.abs(orc.state()))
+        check(np.all(np.abs(got - want) <= 1e-12 * scale), f"grover/{sem}")
+        c.close(); orc.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_GPU_CHECK", "PASS" if int(flag) else "FAIL", flush=True)
+    C.qcs_cuda_dist_finalize()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) else 1)
+
+
+if __name__ == "__main__":
+    main()
