@@ -422,7 +422,7 @@ def main() -> None:
 
 
 # sizeof(PassParams) in qcs_b200/csrc/cuda/common.h: header + 12 segments + 121 gate slots
-PASS_PARAM_BYTES = 48 + 12 * 16 + 121 * 72
+PASS_PARAM_BYTES = 48 + 48 + 2 * 3 * 8 * 8 + 2 * 4 * 8 + 12 * 80 + 145 * 72
 # dram__bytes_read.sum + dram__bytes_write.sum per fused-pass launch, from the ncu --set full
 # captures committed under profiles/ (keyed by local qubits); None where not captured.
 NCU_TRAFFIC_BYTES_PER_LAUNCH = {28: 8.53e9}

@@ -57,6 +57,11 @@ static inline int qcs_op_id_diag_reg(int treg, int creg, int halves) {
 #define QCS_OP_DIAG_FREE_FIRST 160
 #define QCS_OP_DIAG_FREE_LAST 164
 #define QCS_OP_NONE 255
+// Header of a controlled-phase fan: the next `tsel` gate records are diag(1, e^{ia}) gates
+// controlled by various qubits on ONE target; `ctest` = selector of the target bit when it is not
+// a register bit (0xFF otherwise), treg in treg_creg.  The interpreter runs them in a tight loop.
+#define QCS_OP_FAN 250
+#define QCS_MAX_PASS_FANS 24
 // DGate.ctest / DGate.tsel: 0..11 = tile-bit index (per-thread test), QCS_SEL_OUTSIDE | pos =
 // physical position outside the tile (same value for the whole tile), 0xFF = none
 #define QCS_SEL_OUTSIDE 0x40
@@ -73,13 +78,22 @@ struct DGate {
   uint8_t kind;     // GateKind
   int8_t tpos;      // physical position of the target bit
   int8_t cpos;      // physical position of the control bit, -1 if none
-  int8_t treg_creg; // (treg + 1) | (creg + 1) << 4, for plan descriptions
+  uint8_t treg_creg; // (treg + 1) | (creg + 1) << 4
 };
 
 struct DSegment {
   // role r -> tile bit index; roles 0-4 lane bits, then warp bits, the last reg_bits are register bits
   uint8_t role_tilebit[QCS_TILE_BITS];
   uint16_t gate_begin, gate_end;
+  // Host-precomputed per-thread arithmetic (the kernel would otherwise redo it for every tile):
+  uint16_t tb_lut[3][8];               // tile-index bits contributed by thread-id bits [3g, 3g+3)
+  uint16_t toff[QCS_MAX_REG_BITS];     // tile-index offset of each register role bit
+  uint16_t stoff[QCS_MAX_REG_BITS];    // the same, XOR-swizzled
+};
+
+// One contiguous run of non-tile positions: tile-number bits [src, src+len) land at position dst.
+struct DTileRun {
+  uint8_t src, len, dst, pad;
 };
 
 // Kernel parameter block of one pass (passed by value, __grid_constant__).
@@ -90,7 +104,11 @@ struct PassParams {
   int32_t n_segments;
   int32_t n_gates;
   int32_t reg_bits;                    // 4: 256 threads x 16 amplitudes, 3: 512 threads x 8
-  int32_t pad_;
+  int32_t n_tile_runs;
+  DTileRun tile_run[12];               // tile number -> element offset of the tile (bit deposit as runs)
+  // element offsets for the global loads (first segment) and stores (last segment)
+  uint64_t gb_lut[2][3][8];            // [first/last][thread-id bit group][value]
+  uint64_t goff[2][QCS_MAX_REG_BITS];  // [first/last][register role bit]
   DSegment seg[QCS_MAX_PASS_SEGMENTS];
-  DGate gate[QCS_MAX_PASS_GATES + 1];  // +1: the interpreter prefetches one header ahead
+  DGate gate[QCS_MAX_PASS_GATES + QCS_MAX_PASS_FANS + 1];  // fan headers; +1: one-ahead prefetch sentinel
 };

@@ -122,7 +122,7 @@ int dist_swap_positions(Engine &e, int lpos, int gpos) {
   const uint64_t leaving = 1ull - mybit;  // the half whose bit lpos differs from my g-bit leaves
   const uint64_t n_half = e.local_size >> 1;
   const size_t half_bytes = n_half * sizeof(double2);
-  if (!e.staging) CK(cudaMalloc(&e.staging, 2 * half_bytes));
+  if (!e.staging) CK(cudaMalloc(&e.staging, 2 * half_bytes));  // returned to the engine's pool on destroy
   double2 *send_buf = e.staging;
   double2 *recv_buf = e.staging + n_half;
 

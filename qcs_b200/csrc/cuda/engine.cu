@@ -77,12 +77,76 @@ static int load_options(Options &o) {
   if (v == "ldg") o.tile_kernel = 0;
   else if (v == "tma16") o.tile_kernel = 1;
   else if (v == "tma" || v == "tma8") o.tile_kernel = 2;
+  else if (v == "ldg8") o.tile_kernel = 3;
   else if (v.empty()) o.tile_kernel = Options().tile_kernel;
-  else return set_error(QCS_CUDA_ERR_INVALID, "tile_kernel must be ldg|tma|tma16, got '%s'", v.c_str());
+  else return set_error(QCS_CUDA_ERR_INVALID, "tile_kernel must be ldg|ldg8|tma|tma16, got '%s'", v.c_str());
   v = option_value("exchange");
   o.exchange = (v == "p2p") ? 1 : 0;
   return QCS_CUDA_OK;
 }
+
+// ------------------------------------------------------------------ device-buffer pool
+// cudaMalloc / cudaFree of a 16 GiB state cost 10-350 ms each (measured); programs in the
+// reference's style create and destroy circuits freely (every test does), so freed buffers are
+// kept (at most kPoolSlots of them) and handed back to the next qc_create of the same size.
+// QCS_CUDA_POOL=0 disables; an allocation failure trims the pool and retries.
+namespace {
+struct PoolEntry { void *ptr; size_t bytes; int device; };
+std::vector<PoolEntry> g_pool;
+constexpr size_t kPoolSlots = 6;
+constexpr size_t kPoolBytes = (size_t)40 << 30;  // never sit on more than 40 GiB of freed buffers
+bool pool_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *v = std::getenv("QCS_CUDA_POOL");
+    on = (v && (v[0] == '0')) ? 0 : 1;
+  }
+  return on == 1;
+}
+void pool_trim() {
+  for (auto &p : g_pool) cudaFree(p.ptr);
+  g_pool.clear();
+}
+cudaError_t pool_alloc(void **out, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (size_t i = 0; i < g_pool.size(); i++) {
+    if (g_pool[i].bytes == bytes && g_pool[i].device == dev) {
+      *out = g_pool[i].ptr;
+      g_pool.erase(g_pool.begin() + (long)i);
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaErrorMemoryAllocation && !g_pool.empty()) {
+    cudaGetLastError();
+    pool_trim();
+    e = cudaMalloc(out, bytes);
+  }
+  return e;
+}
+void pool_free(void *ptr, size_t bytes) {
+  if (!ptr) return;
+  if (!pool_enabled() || bytes < (1u << 20)) {
+    cudaFree(ptr);
+    return;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes > kPoolBytes) {
+    cudaFree(ptr);
+    return;
+  }
+  g_pool.push_back(PoolEntry{ptr, bytes, dev});
+  size_t total = 0;
+  for (auto &p : g_pool) total += p.bytes;
+  while (g_pool.size() > kPoolSlots || total > kPoolBytes) {  // evict oldest first
+    total -= g_pool.front().bytes;
+    cudaFree(g_pool.front().ptr);
+    g_pool.erase(g_pool.begin());
+  }
+}
+}  // namespace
 
 // ------------------------------------------------------------------ events / stats
 static cudaEvent_t get_event(Engine &e) {
@@ -118,7 +182,7 @@ static void fold_events(Engine &e) {
 // ------------------------------------------------------------------ scratch buffer
 static int ensure_scratch(Engine &e) {
   if (e.scratch || e.opt.dryrun) return QCS_CUDA_OK;
-  CK(cudaMalloc(&e.scratch, e.local_size * sizeof(double2)));
+  CK(pool_alloc((void **)&e.scratch, e.local_size * sizeof(double2)));
   // q_state_init zeroes both buffers (reference src/q_state.c:93-96)
   CK(launch_init_state(e.scratch, e.local_size, false, e.stream));
   e.kernel_launches++;
@@ -176,7 +240,7 @@ static int run_local(Engine &e, const std::vector<PhysGate> &gates, bool record_
     cfg.sem = e.opt.sem;
     cfg.pass_flops_budget = e.opt.pass_flops;
     cfg.direct_io = true;
-    cfg.reg_bits = (e.opt.tile_kernel == 2) ? 3 : 4;
+    cfg.reg_bits = (e.opt.tile_kernel >= 2) ? 3 : 4;
     std::vector<PassPlan> plan = plan_passes(gates, cfg);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e.timing && !e.opt.dryrun && !plan.empty()) {
@@ -191,7 +255,7 @@ static int run_local(Engine &e, const std::vector<PhysGate> &gates, bool record_
       e.passes++;
       e.kernel_launches++;
       e.segments += p.params.n_segments;
-      e.gates_executed += p.params.n_gates;
+      e.gates_executed += p.params.n_gates - p.n_fan_headers;
       const double bytes = 32.0 * (double)e.local_size;
       e.algorithmic_bytes += bytes;
       e.pass_bytes += bytes;
@@ -502,21 +566,33 @@ int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
   if (rc) return fail(rc);
   if ((rc = check_cuda(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate")))
     return fail(rc);
-  if ((rc = check_cuda(cudaMalloc(&e->live, e->local_size * sizeof(double2)), "cudaMalloc(state)")))
+  if ((rc = check_cuda(pool_alloc((void **)&e->live, e->local_size * sizeof(double2)), "cudaMalloc(state)")))
     return fail(rc);
   ReduceWorkspace &ws = e->ws;
   const size_t n_chunks = e->local_size >= SEQ_CHUNK ? e->local_size / SEQ_CHUNK : 1;
   ws.n_chunks_cap = n_chunks;
-  if ((rc = check_cuda(cudaMalloc(&ws.partials, 4 * REDUCE_MAX_BLOCKS * sizeof(double)), "cudaMalloc")) ||
-      (rc = check_cuda(cudaMalloc(&ws.ipartials, REDUCE_MAX_BLOCKS * sizeof(long long)), "cudaMalloc")) ||
-      (rc = check_cuda(cudaMalloc(&ws.result, RES_COUNT * sizeof(double)), "cudaMalloc")) ||
-      (rc = check_cuda(cudaMalloc(&ws.iresult, 4 * sizeof(long long)), "cudaMalloc")) ||
-      (rc = check_cuda(cudaMalloc(&ws.chunk_sum, n_chunks * sizeof(double)), "cudaMalloc")) ||
-      (rc = check_cuda(cudaMalloc(&ws.chunk_approx, (n_chunks + 1) * sizeof(double)), "cudaMalloc")) ||
-      (rc = check_cuda(cudaMalloc(&ws.chunk_delta, n_chunks * sizeof(double)), "cudaMalloc")) ||
-      (rc = check_cuda(cudaMalloc(&ws.chunk_flag, n_chunks), "cudaMalloc")) ||
-      (rc = check_cuda(cudaMalloc(&ws.chunk_exact, (n_chunks + 1) * sizeof(double)), "cudaMalloc")))
-    return fail(rc);
+  {
+    // one slab for every small work array (a dozen cudaMallocs otherwise)
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t sz[] = {up(4 * REDUCE_MAX_BLOCKS * sizeof(double)), up(REDUCE_MAX_BLOCKS * sizeof(long long)),
+                         up(RES_COUNT * sizeof(double)), up(4 * sizeof(long long)),
+                         up(n_chunks * sizeof(double)), up((n_chunks + 1) * sizeof(double)),
+                         up(n_chunks * sizeof(double)), up(n_chunks), up((n_chunks + 1) * sizeof(double))};
+    size_t total = 0;
+    for (size_t b : sz) total += b;
+    e->ws_slab_bytes = total;
+    if ((rc = check_cuda(pool_alloc(&e->ws_slab, total), "cudaMalloc(workspace)"))) return fail(rc);
+    char *p = (char *)e->ws_slab;
+    ws.partials = (double *)p; p += sz[0];
+    ws.ipartials = (long long *)p; p += sz[1];
+    ws.result = (double *)p; p += sz[2];
+    ws.iresult = (long long *)p; p += sz[3];
+    ws.chunk_sum = (double *)p; p += sz[4];
+    ws.chunk_approx = (double *)p; p += sz[5];
+    ws.chunk_delta = (double *)p; p += sz[6];
+    ws.chunk_flag = (unsigned char *)p; p += sz[7];
+    ws.chunk_exact = (double *)p;
+  }
   if ((rc = check_cuda(cudaMemsetAsync(ws.result, 0, RES_COUNT * sizeof(double), e->stream), "cudaMemset")))
     return fail(rc);
   // zero everything, amplitude 0 := 1 (reference src/q_state.c:93-99)
@@ -540,18 +616,10 @@ void qcs_cuda_state_destroy(qcs_cuda_engine *e) {
   for (auto &pr : e->pending_xchg_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);
   for (auto ev : e->markers) if (ev) cudaEventDestroy(ev);
-  cudaFree(e->live);
-  cudaFree(e->scratch);
-  cudaFree(e->staging);
-  cudaFree(e->ws.partials);
-  cudaFree(e->ws.ipartials);
-  cudaFree(e->ws.result);
-  cudaFree(e->ws.iresult);
-  cudaFree(e->ws.chunk_sum);
-  cudaFree(e->ws.chunk_approx);
-  cudaFree(e->ws.chunk_delta);
-  cudaFree(e->ws.chunk_flag);
-  cudaFree(e->ws.chunk_exact);
+  pool_free(e->live, e->local_size * sizeof(double2));
+  pool_free(e->scratch, e->local_size * sizeof(double2));
+  pool_free(e->staging, e->local_size * sizeof(double2));
+  pool_free(e->ws_slab, e->ws_slab_bytes);
   cudaFree(e->u_dev);
   cudaFree(e->idx_dev);
   if (e->stream) cudaStreamDestroy(e->stream);

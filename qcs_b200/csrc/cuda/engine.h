@@ -19,7 +19,7 @@ struct Options {
   bool dryrun = false;
   double pass_flops = 96.0;
   int exchange = 0;  // 0: NCCL send/recv, 1: peer-memory swap kernel
-  int tile_kernel = 0;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8)
+  int tile_kernel = 3;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8), 3: ldg8 (512 thr x 8 amps, plain loads; default)
 };
 
 struct DistContext {
@@ -45,6 +45,8 @@ struct Engine {
   double2 *staging = nullptr;  // half-shard exchange buffer (multi-GPU)
   cudaStream_t stream = nullptr;
   ReduceWorkspace ws{};
+  void *ws_slab = nullptr;       // one allocation backing every array of ws
+  size_t ws_slab_bytes = 0;
   double *u_dev = nullptr;
   long long *idx_dev = nullptr;
   int shots_cap = 0;

@@ -32,12 +32,14 @@
 //              1 copy warp staging tiles through shared memory with TMA bulk copies
 //   2 "tma"    same, 16 compute warps x 8 amplitudes: twice the warps hide the
 //              per-gate dispatch latency
+//   3 "ldg8"   512 threads x 8 amplitudes, plain loads, 2 CTAs per SM (32 warps per SM)
 //
 // Roofline: HBM.  Algorithmic bytes per launch = 32 * 2^nl (every amplitude
 // read once, written once); the planner caps the fused FP64 work per pass so
 // the pass stays bandwidth-bound (DESIGN.md "Kernels").
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "fused_lists.inc"
@@ -222,7 +224,7 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 #define QCS_NREG_STR "8"
 #define QCS_LIST(x) QCS3_##x
 #define QCS_NAME(x) x##_r3
-#define QCS_WITH_LDG 0
+#define QCS_WITH_LDG 1
 #include "fused_body.inc"
 #undef QCS_R
 #undef QCS_CT
@@ -230,6 +232,28 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 #undef QCS_LIST
 #undef QCS_NAME
 #undef QCS_WITH_LDG
+
+// How many tiles ahead a CTA prefetches into L2 (QCS_CUDA_PREFETCH; off by default).
+static uint32_t prefetch_distance() {
+  static int d = -1;
+  if (d < 0) {
+    const char *v = getenv("QCS_CUDA_PREFETCH");
+    d = v ? atoi(v) : 0;  // measured: prefetching ahead into L2 costs ~10 % (profiles/r1_fused_kernel_history.md)
+    if (d < 0) d = 0;
+  }
+  return (uint32_t)d;
+}
+
+// One-off start delay of the second resident CTA of each SM (QCS_CUDA_STAGGER_NS).
+static uint32_t stagger_ns() {
+  static int d = -1;
+  if (d < 0) {
+    const char *v = getenv("QCS_CUDA_STAGGER_NS");
+    d = v ? atoi(v) : 0;
+    if (d < 0) d = 0;
+  }
+  return (uint32_t)d;
+}
 
 static int tile_row_bits(const PassParams &p) {
   int b = 0;
@@ -243,9 +267,9 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
                               cudaStream_t stream, int variant) {
   const unsigned n_tiles = 1u << (n_local - QCS_TILE_BITS);
   static int sm_count = 0;
-  static bool configured[3] = {false, false, false};
-  if (variant < 0 || variant > 2) return cudaErrorInvalidValue;
-  if ((variant == 2) != (params.reg_bits == 3)) return cudaErrorInvalidValue;
+  static bool configured[4] = {false, false, false, false};
+  if (variant < 0 || variant > 3) return cudaErrorInvalidValue;
+  if ((variant >= 2) != (params.reg_bits == 3)) return cudaErrorInvalidValue;
   if (sm_count == 0) {
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -254,9 +278,7 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
     if (e != cudaSuccess) return e;
     sm_count = sms;
   }
-  // slots + barriers/origins + per-thread tile bits of every segment (uint16 [segment][thread])
-  const size_t smem_tma = (size_t)kSlots * kTileBytes + 128 +
-                          (size_t)QCS_MAX_PASS_SEGMENTS * (variant == 2 ? 512 : 256) * 2;
+  const size_t smem_tma = (size_t)kSlots * kTileBytes + 128;  // slots + barriers + tile origins
   const size_t smem_ldg = (size_t)kTileBytes;
   if (!configured[variant]) {
     cudaError_t e;
@@ -266,21 +288,26 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
     else if (variant == 1)
       e = cudaFuncSetAttribute(fused_pass_tma_r4, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem_tma);
-    else
+    else if (variant == 2)
       e = cudaFuncSetAttribute(fused_pass_tma_r3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem_tma);
+    else
+      e = cudaFuncSetAttribute(fused_pass_ldg_r3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem_ldg);
     if (e != cudaSuccess) return e;
     configured[variant] = true;
   }
   const unsigned grid = n_tiles < (unsigned)sm_count ? n_tiles : (unsigned)sm_count;
   if (variant == 0) {
-    fused_pass_ldg_r4<<<n_tiles, 256, smem_ldg, stream>>>(state, params);
+    fused_pass_ldg_r4<<<n_tiles, 256, smem_ldg, stream>>>(state, params, prefetch_distance(), stagger_ns(), (uint32_t)sm_count);
   } else if (variant == 1) {
     fused_pass_tma_r4<<<grid, 256 + 32, smem_tma, stream>>>(state, params, n_tiles,
                                                             (uint32_t)tile_row_bits(params));
-  } else {
+  } else if (variant == 2) {
     fused_pass_tma_r3<<<grid, 512 + 32, smem_tma, stream>>>(state, params, n_tiles,
                                                             (uint32_t)tile_row_bits(params));
+  } else {
+    fused_pass_ldg_r3<<<n_tiles, 512, smem_ldg, stream>>>(state, params, prefetch_distance(), stagger_ns(), (uint32_t)sm_count);
   }
   return cudaGetLastError();
 }

@@ -228,35 +228,62 @@ struct PassBuilder {
       }
     }
     pp.n_segments = (int)segs.size();
-    pp.n_gates = (int)gates.size();
     pp.reg_bits = cfg.reg_bits;
+    // A bit that is not a register bit is tested once per thread (lane / warp tile
+    // bits: encoded as the tile-bit index) or once per tile (positions outside the
+    // tile: QCS_SEL_OUTSIDE | physical position).
+    auto encode_sel = [&](int pos, int tilebit) -> uint8_t {
+      return tilebit >= 0 ? (uint8_t)tilebit : (uint8_t)(QCS_SEL_OUTSIDE | pos);
+    };
+    auto is_cphase = [](const PhysGate &g) {
+      return g.c.kind == GK_DIAG && g.cpos >= 0 && (g.c.flags & GF_D0_IDENT) &&
+             !(g.c.flags & GF_D1_IDENT);
+    };
+    int out_n = 0, n_fans = 0, fan_left = 0;
     for (int si = 0; si < (int)segs.size(); si++) {
       DSegment &ds = pp.seg[si];
       assign_roles(segs[si].regbits, ds.role_tilebit);
-      ds.gate_begin = (uint16_t)segs[si].begin;
-      ds.gate_end = (uint16_t)segs[si].end;
+      ds.gate_begin = (uint16_t)out_n;
+      auto reg_of = [&](int pos) -> int {
+        const int tbit = pos >= 0 ? tilebit_of(pos) : -1;
+        for (int k = 0; k < cfg.reg_bits; k++)
+          if (tbit >= 0 && segs[si].regbits[k] == tbit) return k;
+        return -1;
+      };
       for (int gi = segs[si].begin; gi < segs[si].end; gi++) {
         const PhysGate &g = gates[gi];
-        DGate &dg = pp.gate[gi];
+        const int treg = reg_of(g.tpos), creg = reg_of(g.cpos);
+        const int tb = tilebit_of(g.tpos);
+        const int cb = g.cpos >= 0 ? tilebit_of(g.cpos) : -1;
+        // Controlled-phase fan: a run of >= 3 consecutive controlled diag(1, e^{ia}) gates on one
+        // target gets a header so the kernel walks it in a tight loop (QFT: one fan per round).
+        if (is_cphase(g) && n_fans < QCS_MAX_PASS_FANS) {
+          int run = 1;
+          while (gi + run < segs[si].end && is_cphase(gates[gi + run]) &&
+                 gates[gi + run].tpos == g.tpos && run < 120)
+            run++;
+          if (run >= 3 && fan_left == 0) {
+            DGate &hd = pp.gate[out_n++];
+            std::memset(&hd, 0, sizeof(hd));
+            hd.op = QCS_OP_FAN;
+            hd.kind = GK_DIAG;
+            hd.tsel = (uint8_t)run;  // number of entries that follow
+            hd.ctest = treg < 0 ? encode_sel(g.tpos, tb) : 0xFF;
+            hd.tpos = (int8_t)g.tpos;
+            hd.cpos = -1;
+            hd.treg_creg = (uint8_t)(treg + 1);
+            n_fans++;
+            fan_left = run;
+          }
+        }
+        if (fan_left > 0) fan_left--;
+        DGate &dg = pp.gate[out_n++];
         std::memcpy(dg.m, g.c.m, sizeof(dg.m));
         dg.kind = g.c.kind;
         dg.flags = g.c.flags;
         dg.tpos = (int8_t)g.tpos;
         dg.cpos = (int8_t)g.cpos;
-        int treg = -1, creg = -1;
-        int tb = tilebit_of(g.tpos);
-        int cb = g.cpos >= 0 ? tilebit_of(g.cpos) : -1;
-        for (int k = 0; k < cfg.reg_bits; k++) {
-          if (tb >= 0 && segs[si].regbits[k] == tb) treg = k;
-          if (cb >= 0 && segs[si].regbits[k] == cb) creg = k;
-        }
-        dg.treg_creg = (int8_t)((treg + 1) | ((creg + 1) << 4));
-        // A bit that is not a register bit is tested once per thread (lane / warp
-        // tile bits: encoded as the tile-bit index) or once per tile (positions
-        // outside the tile: QCS_SEL_OUTSIDE | physical position).
-        auto encode_sel = [&](int pos, int tilebit) -> uint8_t {
-          return tilebit >= 0 ? (uint8_t)tilebit : (uint8_t)(QCS_SEL_OUTSIDE | pos);
-        };
+        dg.treg_creg = (uint8_t)((treg + 1) | ((creg + 1) << 4));
         dg.ctest = (g.cpos >= 0 && creg < 0) ? encode_sel(g.cpos, cb) : 0xFF;
         dg.tsel = 0xFF;
         const int row0 = (g.c.flags & GF_ROW0_ONLY) ? 1 : 0;
@@ -277,12 +304,62 @@ struct PassBuilder {
           default: dg.op = QCS_OP_NONE; break;
         }
       }
+      ds.gate_end = (uint16_t)out_n;
+    }
+    pp.n_gates = out_n;
+    plan.n_fan_headers = n_fans;
+    // ---- tables that spare the kernel its per-tile index arithmetic ----------------------
+    auto swz = [](uint32_t slot) { return slot ^ (((slot >> 3) ^ (slot >> 6) ^ (slot >> 9)) & 7u); };
+    const int thread_roles = QCS_TILE_BITS - cfg.reg_bits;
+    for (int si = 0; si < (int)segs.size(); si++) {
+      DSegment &ds = pp.seg[si];
+      for (int g = 0; g < 3; g++)
+        for (int v = 0; v < 8; v++) {
+          uint32_t tb = 0;
+          for (int j = 0; j < 3; j++) {
+            const int role = 3 * g + j;
+            if (role < thread_roles && ((v >> j) & 1)) tb |= 1u << ds.role_tilebit[role];
+          }
+          ds.tb_lut[g][v] = (uint16_t)tb;
+        }
+      for (int k = 0; k < cfg.reg_bits; k++) {
+        const uint32_t off = 1u << ds.role_tilebit[thread_roles + k];
+        ds.toff[k] = (uint16_t)off;
+        ds.stoff[k] = (uint16_t)swz(off);
+      }
+    }
+    for (int which = 0; which < 2; which++) {
+      const DSegment &ds = pp.seg[which == 0 ? 0 : (int)segs.size() - 1];
+      for (int g = 0; g < 3; g++)
+        for (int v = 0; v < 8; v++) {
+          uint64_t off = 0;
+          for (int b = 0; b < QCS_TILE_BITS; b++)
+            if ((ds.tb_lut[g][v] >> b) & 1) off |= 1ull << pp.tile_pos[b];
+          pp.gb_lut[which][g][v] = off;
+        }
+      for (int k = 0; k < cfg.reg_bits; k++)
+        pp.goff[which][k] = 1ull << pp.tile_pos[ds.role_tilebit[thread_roles + k]];
+    }
+    {
+      int n_runs = 0, src = 0, p = 0;
+      while (p < cfg.n_local) {
+        if (!((pp.nontile_mask >> p) & 1ull)) { p++; continue; }
+        int len = 0;
+        while (p + len < cfg.n_local && ((pp.nontile_mask >> (p + len)) & 1ull)) len++;
+        pp.tile_run[n_runs].src = (uint8_t)src;
+        pp.tile_run[n_runs].len = (uint8_t)len;
+        pp.tile_run[n_runs].dst = (uint8_t)p;
+        n_runs++;
+        src += len;
+        p += len;
+      }
+      pp.n_tile_runs = n_runs;  // <= 8: seven tile bits above position 4 split the rest into <= 8 runs
     }
     // sentinel header read by the interpreter's one-ahead prefetch
-    std::memset(&pp.gate[gates.size()], 0, sizeof(DGate));
-    pp.gate[gates.size()].op = QCS_OP_NONE;
-    pp.gate[gates.size()].ctest = 0xFF;
-    pp.gate[gates.size()].tsel = 0xFF;
+    std::memset(&pp.gate[out_n], 0, sizeof(DGate));
+    pp.gate[out_n].op = QCS_OP_NONE;
+    pp.gate[out_n].ctest = 0xFF;
+    pp.gate[out_n].tsel = 0xFF;
     plan.n_gates_api = n_api;
     plan.flops_per_amp = flops;
     return plan;
@@ -338,6 +415,11 @@ std::string describe_plan(const std::vector<PassPlan> &passes) {
       s += buf;
       for (int gi = ds.gate_begin; gi < ds.gate_end; gi++) {
         const DGate &g = pp.gate[gi];
+        if (g.op == QCS_OP_FAN) {
+          std::snprintf(buf, sizeof(buf), " fan[%d]", (int)g.tsel);
+          s += buf;
+          continue;
+        }
         if (g.cpos >= 0)
           std::snprintf(buf, sizeof(buf), " %s(c%d,t%d)", kind_name[g.kind], g.cpos, g.tpos);
         else

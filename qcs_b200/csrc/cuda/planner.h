@@ -37,6 +37,7 @@ Classified classify_gate(const double m[8], bool controlled, Semantics sem);
 struct PassPlan {
   PassParams params;
   int n_gates_api;          // API-level gates folded into this pass (incl. NOPs)
+  int n_fan_headers = 0;    // fan header records among params.n_gates (not gates)
   double flops_per_amp;     // planner's cost estimate
   std::vector<int> tile_positions;
 };

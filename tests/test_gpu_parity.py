@@ -80,7 +80,7 @@ def _random_script(rng, n, length, generic=True):
     return s
 
 
-@pytest.mark.parametrize("tile_kernel", ["tma", "tma16", "ldg"])
+@pytest.mark.parametrize("tile_kernel", ["tma", "tma16", "ldg", "ldg8"])
 @pytest.mark.parametrize("sem", ["reference", "corrected"])
 @pytest.mark.parametrize("n", [12, 13, 15, 17, 21])
 def test_fused_random_circuits_bit_exact(n, sem, tile_kernel):
@@ -101,7 +101,7 @@ def test_fused_random_circuits_bit_exact(n, sem, tile_kernel):
         orc.close(); c.close()
 
 
-@pytest.mark.parametrize("tile_kernel", ["tma", "tma16", "ldg"])
+@pytest.mark.parametrize("tile_kernel", ["tma", "tma16", "ldg", "ldg8"])
 @pytest.mark.parametrize("sem", ["reference", "corrected"])
 def test_every_target_control_pair(sem, tile_kernel):
     """Each (control, target) placement -- lane, warp, register, outside-tile bits -- for each gate class."""

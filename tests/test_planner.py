@@ -42,7 +42,7 @@ def _parse(text):
 PAIRING = {"generic", "real", "hsym", "swap"}
 
 
-@pytest.mark.parametrize("tile_kernel,reg_bits", [("tma", 3), ("tma16", 4), ("ldg", 4)])
+@pytest.mark.parametrize("tile_kernel,reg_bits", [("tma", 3), ("tma16", 4), ("ldg", 4), ("ldg8", 3)])
 @pytest.mark.parametrize("n", [12, 20, 30, 34])
 def test_plan_invariants_random_circuit(n, tile_kernel, reg_bits):
     script = po.random_circuit_script(n, 6)
