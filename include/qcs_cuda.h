@@ -100,7 +100,8 @@ int qcs_cuda_write_amplitudes(qcs_cuda_engine *e, int which, long first,
 
 /* ---- configuration / introspection ------------------------------------------------ */
 /* Keys: "semantics" = reference|corrected, "fusion" = on|off,
- * "dryrun" = 0|1, "pass_flops" = <float>, "tile_kernel" = ldg|tma|tma16.
+ * "dryrun" = 0|1, "pass_flops" = <float>, "tile_kernel" = ldg8|ldg|tma|tma16,
+ * "exchange" = p2p|nccl (multi-GPU position swaps: in-place peer-memory kernel, or NCCL send/recv).
  * Defaults come from QCS_CUDA_<KEY> in the environment; set_default applies
  * to engines created afterwards. */
 int qcs_cuda_set_default(const char *key, const char *value);

@@ -110,11 +110,104 @@ unpack_half_kernel(double2 *__restrict__ live, const double2 *__restrict__ stagi
   }
 }
 
+// In-place position swap over NVLink peer memory: pair j = (my element with bit lpos ==
+// `leaving`, the partner's element with the opposite bit).  Each rank handles half of the pairs
+// (`share`), reading one side remotely and writing one side remotely, so both directions of the
+// link carry 8 * 2^nl bytes -- the minimum -- and no staging buffer or pack/unpack pass exists.
+__global__ void __launch_bounds__(256)
+p2p_swap_kernel(double2 *__restrict__ mine, double2 *__restrict__ peer, uint64_t pairs_begin,
+                uint64_t pairs_end, int pos, uint64_t leaving) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t bit = 1ull << pos;
+  for (uint64_t j = pairs_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < pairs_end;
+       j += stride) {
+    const uint64_t low = j & (bit - 1ull);
+    const uint64_t i = (((j >> pos) << (pos + 1)) | low) | (leaving << pos);
+    const uint64_t ip = i ^ bit;
+    const double2 a = mine[i];
+    const double2 b = peer[ip];
+    mine[i] = b;
+    peer[ip] = a;
+  }
+}
+
 }  // namespace
+
+// Exchanges CUDA IPC handles of every rank's state buffer so that partners can address it.
+int dist_open_peers(Engine &e) {
+  DistContext &d = dist();
+  if (!d.active || e.opt.dryrun) return QCS_CUDA_OK;
+  cudaIpcMemHandle_t mine;
+  CK(cudaIpcGetMemHandle(&mine, e.live));
+  std::vector<cudaIpcMemHandle_t> all(d.world);
+  int rc = dist_allgather_host(&mine, all.data(), sizeof(mine));
+  if (rc) return rc;
+  e.peer_live.assign(d.world, nullptr);
+  for (int r = 0; r < d.world; r++) {
+    if (r == d.rank) {
+      e.peer_live[r] = e.live;
+      continue;
+    }
+    void *ptr = nullptr;
+    cudaError_t ce = cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (ce != cudaSuccess) {
+      cudaGetLastError();
+      e.peer_live.clear();  // no peer access: the NCCL path stays in charge
+      return QCS_CUDA_OK;
+    }
+    e.peer_live[r] = (double2 *)ptr;
+  }
+  return QCS_CUDA_OK;
+}
+
+void dist_close_peers(Engine &e) {
+  DistContext &d = dist();
+  for (int r = 0; r < (int)e.peer_live.size(); r++)
+    if (r != d.rank && e.peer_live[r]) cudaIpcCloseMemHandle(e.peer_live[r]);
+  e.peer_live.clear();
+}
+
+static int stream_barrier(Engine &e) {
+  // a 4-byte all-reduce on the engine's stream: completes only once every rank's stream got here
+  DistContext &d = dist();
+  int *flag = (int *)((char *)g_small_dev + kSmallBytes - 64);  // clear of dist_allgather_host's area
+  NK(ncclAllReduce(flag, flag, 1, ncclInt, ncclSum, (ncclComm_t)d.comm, e.stream));
+  return QCS_CUDA_OK;
+}
+
+static int p2p_swap_positions(Engine &e, int lpos, int gpos) {
+  DistContext &d = dist();
+  const int gbit = gpos - e.nl;
+  const int partner = d.rank ^ (1 << gbit);
+  const uint64_t mybit = (uint64_t)((d.rank >> gbit) & 1);
+  const uint64_t n_half = e.local_size >> 1;
+  const uint64_t begin = mybit ? n_half / 2 : 0, end = mybit ? n_half : n_half / 2;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (e.timing) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, e.stream);
+  }
+  int rc = stream_barrier(e);  // the partner finished its previous pass on the data I will touch
+  if (rc) return rc;
+  p2p_swap_kernel<<<148 * 16, 256, 0, e.stream>>>(e.live, e.peer_live[partner], begin, end, lpos,
+                                                  1ull - mybit);
+  CK(cudaGetLastError());
+  e.kernel_launches++;
+  rc = stream_barrier(e);      // nobody reads swapped data before both halves of the pairs are done
+  if (rc) return rc;
+  if (ev0) {
+    cudaEventRecord(ev1, e.stream);
+    e.pending_xchg_events.emplace_back(ev0, ev1);
+  }
+  return QCS_CUDA_OK;
+}
 
 int dist_swap_positions(Engine &e, int lpos, int gpos) {
   DistContext &d = dist();
   if (!d.active) return set_error(QCS_CUDA_ERR_INVALID, "global position without a communicator");
+  if (e.opt.exchange == 1 && e.opt.sem == SEM_CORRECTED && !e.peer_live.empty())
+    return p2p_swap_positions(e, lpos, gpos);
   ncclComm_t comm = (ncclComm_t)d.comm;
   const int gbit = gpos - e.nl;
   const int partner = d.rank ^ (1 << gbit);
@@ -182,7 +275,7 @@ int dist_allgather_host(const void *mine, void *all, size_t bytes_each) {
     std::memcpy(all, mine, bytes_each);
     return QCS_CUDA_OK;
   }
-  if (bytes_each * (size_t)(d.world + 1) > kSmallBytes)
+  if (bytes_each * (size_t)(d.world + 1) > kSmallBytes - 64)
     return set_error(QCS_CUDA_ERR_INVALID, "dist_allgather_host: payload too large");
   char *dev = (char *)g_small_dev;
   char *dev_all = dev + bytes_each;

@@ -81,7 +81,9 @@ static int load_options(Options &o) {
   else if (v.empty()) o.tile_kernel = Options().tile_kernel;
   else return set_error(QCS_CUDA_ERR_INVALID, "tile_kernel must be ldg|ldg8|tma|tma16, got '%s'", v.c_str());
   v = option_value("exchange");
-  o.exchange = (v == "p2p") ? 1 : 0;
+  if (v == "nccl") o.exchange = 0;
+  else if (v.empty() || v == "p2p") o.exchange = 1;
+  else return set_error(QCS_CUDA_ERR_INVALID, "exchange must be p2p|nccl, got '%s'", v.c_str());
   return QCS_CUDA_OK;
 }
 
@@ -601,6 +603,7 @@ int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
     return fail(rc);
   e->kernel_launches++;
   if ((rc = check_cuda(cudaStreamSynchronize(e->stream), "init sync"))) return fail(rc);
+  if (d.active && e->opt.exchange == 1 && (rc = dist_open_peers(*e))) return fail(rc);
   *out = e;
   return QCS_CUDA_OK;
 }
@@ -612,6 +615,10 @@ void qcs_cuda_state_destroy(qcs_cuda_engine *e) {
     return;
   }
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (!e->peer_live.empty()) {
+    dist_barrier(*e);  // nobody still addresses this buffer
+    dist_close_peers(*e);
+  }
   for (auto &pr : e->pending_pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto &pr : e->pending_xchg_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);

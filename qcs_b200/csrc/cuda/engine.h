@@ -42,7 +42,8 @@ struct Engine {
 
   double2 *live = nullptr;     // reference: state->vector
   double2 *scratch = nullptr;  // reference: state->scratch_vector (lazily allocated)
-  double2 *staging = nullptr;  // half-shard exchange buffer (multi-GPU)
+  double2 *staging = nullptr;  // half-shard exchange buffer (multi-GPU, NCCL path)
+  std::vector<double2 *> peer_live;  // every rank's state buffer mapped through CUDA IPC (P2P path)
   cudaStream_t stream = nullptr;
   ReduceWorkspace ws{};
   void *ws_slab = nullptr;       // one allocation backing every array of ws
@@ -83,6 +84,8 @@ int dist_allreduce_sum(Engine &e, double *dev_values, int count);
 int dist_allreduce_max_i64(Engine &e, long long *dev_values, size_t count);
 int dist_allgather_host(const void *mine, void *all, size_t bytes_each);
 int dist_barrier(Engine &e);
+int dist_open_peers(Engine &e);
+void dist_close_peers(Engine &e);
 
 }  // namespace qcs
 

@@ -38,9 +38,9 @@ def main():
             ok = False
             print(f"[rank {rank}] FAIL {msg}", flush=True)
 
-    for fusion in ("on", "off"):
+    for fusion, exchange in (("on", "p2p"), ("on", "nccl"), ("off", "p2p")):
         for name, (n, sem, script) in CASES.items():
-            c = Circuit(n, semantics=sem, fusion=fusion)
+            c = Circuit(n, semantics=sem, fusion=fusion, exchange=exchange)
             orc = po.Oracle(n, sem)
             po.replay(c, script); po.replay(orc, script)
             c.flush(); st = c.stats()
@@ -61,7 +61,7 @@ def main():
             got = c.state(); want = orc.state()[first:first + count]
             check(np.all(got == want), f"{name}/{fusion}: post-measurement shard differs")
             if rank == 0:
-                print(f"done {name}/{fusion}: passes={st['passes']} remaps={st['remaps']}", flush=True)
+                print(f"done {name}/{fusion}/{exchange}: passes={st['passes']} remaps={st['remaps']}", flush=True)
             c.close(); orc.close()
     # Grover across ranks (allreduced diffusion mean): tolerance 1e-12
     for sem in ("corrected", "reference"):
