@@ -256,6 +256,7 @@ def main() -> None:
     ap.add_argument("--pass-flops", type=float, default=None)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-aux", action="store_true")
+    ap.add_argument("--aux", action="store_true", help="also run the random-circuit config at N=1 (31 qubits)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -356,7 +357,7 @@ def main() -> None:
     h2d_per_step = int(passes_per_step * PASS_PARAM_BYTES)
 
     aux = None
-    if world > 1 and not args.skip_aux:
+    if (world > 1 or args.aux) and not args.skip_aux:
         aux = random_circuit_aux(Circuit, kw, world, barrier, dist, torch)
 
     if rank != 0:
@@ -446,11 +447,13 @@ def random_circuit_aux(Circuit, kw, world, barrier, dist, torch) -> dict:
     dev_s = c.marker_elapsed_ms(0, 1) * 1e-3
     st = c.stats()
     c.close()
-    t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_s = float(t[0])
+    if world > 1:
+        t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s = float(t[0])
     return {"workload": f"{n}-qubit random circuit (H/RZ/CNOT brickwork, depth 40, {len(script)} gates)",
             "gates_per_s": len(script) / dev_s, "seconds": dev_s, "passes": st["passes"],
+            "amplitude_gate_updates_per_s_per_gpu": len(script) * 2.0 ** n / dev_s / world,
             "remaps": st["remaps"], "exchange_ms": st["exchange_ms"], "pass_ms": st["pass_ms"],
             "pass_GBps": st["pass_bytes"] / (st["pass_ms"] * 1e-3) / 1e9 if st["pass_ms"] else None,
             "exchange_GBps_per_direction": (st["exchange_bytes"] / (st["exchange_ms"] * 1e-3) / 1e9

@@ -110,17 +110,30 @@ unpack_half_kernel(double2 *__restrict__ live, const double2 *__restrict__ stagi
   }
 }
 
+// same descriptor as kernels_fused.cu slice_expand, here in pair-index space
+__device__ __forceinline__ uint64_t slice_expand_pairs(uint64_t dense, uint64_t desc) {
+  const uint32_t count = (uint32_t)(desc >> 24) & 0xffu;
+  const uint32_t value = (uint32_t)(desc >> 32);
+  for (uint32_t b = 0; b < count; b++) {
+    const uint32_t pos = (uint32_t)(desc >> (8 * b)) & 0xffu;
+    const uint64_t low = dense & ((1ull << pos) - 1ull);
+    dense = ((dense >> pos) << (pos + 1)) | low | ((uint64_t)((value >> b) & 1u) << pos);
+  }
+  return dense;
+}
+
 // In-place position swap over NVLink peer memory: pair j = (my element with bit lpos ==
 // `leaving`, the partner's element with the opposite bit).  Each rank handles half of the pairs
 // (`share`), reading one side remotely and writing one side remotely, so both directions of the
 // link carry 8 * 2^nl bytes -- the minimum -- and no staging buffer or pack/unpack pass exists.
 __global__ void __launch_bounds__(256)
 p2p_swap_kernel(double2 *__restrict__ mine, double2 *__restrict__ peer, uint64_t pairs_begin,
-                uint64_t pairs_end, int pos, uint64_t leaving) {
+                uint64_t pairs_end, int pos, uint64_t leaving, uint64_t slice) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t bit = 1ull << pos;
-  for (uint64_t j = pairs_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < pairs_end;
-       j += stride) {
+  for (uint64_t m = pairs_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < pairs_end;
+       m += stride) {
+    const uint64_t j = slice_expand_pairs(m, slice);  // dense index inside the slice -> pair index
     const uint64_t low = j & (bit - 1ull);
     const uint64_t i = (((j >> pos) << (pos + 1)) | low) | (leaving << pos);
     const uint64_t ip = i ^ bit;
@@ -167,37 +180,46 @@ void dist_close_peers(Engine &e) {
   e.peer_live.clear();
 }
 
-static int stream_barrier(Engine &e) {
-  // a 4-byte all-reduce on the engine's stream: completes only once every rank's stream got here
+static int stream_barrier(Engine &e, cudaStream_t stream) {
+  // a 4-byte all-reduce on `stream`: completes only once every rank's stream got here
   DistContext &d = dist();
   int *flag = (int *)((char *)g_small_dev + kSmallBytes - 64);  // clear of dist_allgather_host's area
-  NK(ncclAllReduce(flag, flag, 1, ncclInt, ncclSum, (ncclComm_t)d.comm, e.stream));
+  NK(ncclAllReduce(flag, flag, 1, ncclInt, ncclSum, (ncclComm_t)d.comm, stream));
+  (void)e;
   return QCS_CUDA_OK;
 }
 
-static int p2p_swap_positions(Engine &e, int lpos, int gpos) {
+bool dist_p2p_available(const Engine &e) {
+  return dist().active && e.opt.exchange == 1 && e.opt.sem == SEM_CORRECTED && !e.peer_live.empty();
+}
+
+// One slice of an in-place position swap on `stream` (slice = 0: the whole shard).  The slice
+// descriptor lives in pair-index space (the local index with bit lpos removed).
+int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos, uint64_t slice) {
   DistContext &d = dist();
   const int gbit = gpos - e.nl;
   const int partner = d.rank ^ (1 << gbit);
   const uint64_t mybit = (uint64_t)((d.rank >> gbit) & 1);
-  const uint64_t n_half = e.local_size >> 1;
-  const uint64_t begin = mybit ? n_half / 2 : 0, end = mybit ? n_half : n_half / 2;
+  const unsigned slice_bits = (unsigned)(slice >> 24) & 0xffu;
+  const uint64_t n_pairs = (e.local_size >> 1) >> slice_bits;
+  const uint64_t begin = mybit ? n_pairs / 2 : 0, end = mybit ? n_pairs : n_pairs / 2;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (e.timing) {
     cudaEventCreate(&ev0);
     cudaEventCreate(&ev1);
-    cudaEventRecord(ev0, e.stream);
+    cudaEventRecord(ev0, stream);
   }
-  int rc = stream_barrier(e);  // the partner finished its previous pass on the data I will touch
+  int rc = stream_barrier(e, stream);  // the partner finished its previous work on these elements
   if (rc) return rc;
-  p2p_swap_kernel<<<148 * 16, 256, 0, e.stream>>>(e.live, e.peer_live[partner], begin, end, lpos,
-                                                  1ull - mybit);
+  const unsigned blocks = slice_bits ? 148 * 8 : 148 * 16;
+  p2p_swap_kernel<<<blocks, 256, 0, stream>>>(e.live, e.peer_live[partner], begin, end, lpos,
+                                              1ull - mybit, slice);
   CK(cudaGetLastError());
   e.kernel_launches++;
-  rc = stream_barrier(e);      // nobody reads swapped data before both halves of the pairs are done
+  rc = stream_barrier(e, stream);      // nobody reads swapped data before both halves of the pairs are done
   if (rc) return rc;
   if (ev0) {
-    cudaEventRecord(ev1, e.stream);
+    cudaEventRecord(ev1, stream);
     e.pending_xchg_events.emplace_back(ev0, ev1);
   }
   return QCS_CUDA_OK;
@@ -206,8 +228,7 @@ static int p2p_swap_positions(Engine &e, int lpos, int gpos) {
 int dist_swap_positions(Engine &e, int lpos, int gpos) {
   DistContext &d = dist();
   if (!d.active) return set_error(QCS_CUDA_ERR_INVALID, "global position without a communicator");
-  if (e.opt.exchange == 1 && e.opt.sem == SEM_CORRECTED && !e.peer_live.empty())
-    return p2p_swap_positions(e, lpos, gpos);
+  if (dist_p2p_available(e)) return dist_p2p_swap(e, e.stream, lpos, gpos, 0);
   ncclComm_t comm = (ncclComm_t)d.comm;
   const int gbit = gpos - e.nl;
   const int partner = d.rank ^ (1 << gbit);

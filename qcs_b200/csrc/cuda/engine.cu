@@ -72,7 +72,7 @@ static int load_options(Options &o) {
   o.dryrun = (v == "1" || v == "on");
   v = option_value("pass_flops");
   if (!v.empty()) o.pass_flops = std::atof(v.c_str());
-  if (!(o.pass_flops > 0)) o.pass_flops = 96.0;
+  if (!(o.pass_flops > 0)) o.pass_flops = Options().pass_flops;
   v = option_value("tile_kernel");
   if (v == "ldg") o.tile_kernel = 0;
   else if (v == "tma16") o.tile_kernel = 1;

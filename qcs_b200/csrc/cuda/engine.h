@@ -17,7 +17,7 @@ struct Options {
   Semantics sem = SEM_REFERENCE;
   bool fusion = true;
   bool dryrun = false;
-  double pass_flops = 96.0;
+  double pass_flops = 200.0;  // FP64 work per amplitude a pass may fuse (measured optimum: scripts/budget_sweep.py)
   int exchange = 0;  // 0: NCCL send/recv, 1: peer-memory swap kernel
   int tile_kernel = 3;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8), 3: ldg8 (512 thr x 8 amps, plain loads; default)
 };
@@ -45,6 +45,8 @@ struct Engine {
   double2 *staging = nullptr;  // half-shard exchange buffer (multi-GPU, NCCL path)
   std::vector<double2 *> peer_live;  // every rank's state buffer mapped through CUDA IPC (P2P path)
   cudaStream_t stream = nullptr;
+  cudaStream_t xstream = nullptr;  // exchanges pipelined against passes (multi-GPU)
+  cudaEvent_t slice_done[8] = {}, slice_swapped[8] = {}, slice_start = nullptr;
   ReduceWorkspace ws{};
   void *ws_slab = nullptr;       // one allocation backing every array of ws
   size_t ws_slab_bytes = 0;
@@ -85,6 +87,8 @@ int dist_allreduce_max_i64(Engine &e, long long *dev_values, size_t count);
 int dist_allgather_host(const void *mine, void *all, size_t bytes_each);
 int dist_barrier(Engine &e);
 int dist_open_peers(Engine &e);
+bool dist_p2p_available(const Engine &e);
+int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos, uint64_t slice);
 void dist_close_peers(Engine &e);
 
 }  // namespace qcs

@@ -10,8 +10,10 @@ namespace qcs {
 // kernels_fused.cu ----------------------------------------------------------
 // variant 0: one CTA per tile, plain 128-bit global loads/stores
 // variant 1: persistent CTAs, tiles staged through shared memory by TMA bulk copies
+// slice: 0 = the whole shard; else a slice descriptor (kernels_fused.cu slice_expand) in tile-number
+// space -- only those tiles are processed (ldg variants), for pipelining passes with exchanges.
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
-                              cudaStream_t stream, int variant);
+                              cudaStream_t stream, int variant, uint64_t slice = 0);
 
 // kernels_simple.cu: one launch per gate (fusion off, shards below one tile) ---
 cudaError_t launch_simple_gate(double2 *state, const DGate &g, int n_local,
