@@ -40,11 +40,12 @@ def _newer(target: str, deps: list[str]) -> bool:
 def _generate() -> None:
     """fused_lists.inc (register lists + the per-gate dispatch switch) from its generator."""
     gen = os.path.join(CUDA_SRC, "gen_fused_lists.py")
-    inc = os.path.join(CUDA_SRC, "fused_lists.inc")
-    if _newer(inc, [gen]):
-        text = subprocess.check_output([sys.executable, gen], text=True)
-        with open(inc, "w") as f:
-            f.write(text)
+    for what, name in (("lists", "fused_lists.inc"), ("ops", "fused_ops.h")):
+        inc = os.path.join(CUDA_SRC, name)
+        if _newer(inc, [gen]):
+            text = subprocess.check_output([sys.executable, gen, what], text=True)
+            with open(inc, "w") as f:
+                f.write(text)
 
 
 def _headers() -> list[str]:

@@ -39,47 +39,59 @@ enum GateKind : uint8_t {
 enum GateFlags : uint8_t {
   GF_ROW0_ONLY = 1,   // reference-semantics controlled gate: only the target=0 row is written
   GF_D0_IDENT = 2,    // diagonal entry 0 is exactly (1,0): untouched
-  GF_D1_IDENT = 4     // diagonal entry 1 is exactly (1,0): untouched
+  GF_D1_IDENT = 4,    // diagonal entry 1 is exactly (1,0): untouched
+  GF_FAN_HEADER = 0x80  // not a gate: header record of a controlled-phase fan (below)
 };
 
-// Dispatch ids: the `op` byte of a DGate selects one straight-line block of the
-// generated switch (gen_fused_lists.py emits the cases with the same formulas).
+// Dispatch ids.  The formulas below give SYMBOLIC ids; DGate.op holds the case label the generator
+// assigned to that id (fused_ops.h, QCS<R>_CASE_LABEL[symbolic]): the index into the interpreter's
+// brx.idx jump table.
 //   kind_index: 0 HSYM, 1 REAL, 2 SWAP, 3 GENERIC;  treg/creg: register-role index, creg -1 = none
 static inline int qcs_op_id_pair(int kind_index, int row0, int treg, int creg) {
   return ((kind_index * 2 + row0) * 4 + treg) * 5 + (creg + 1);
 }
-// diagonal whose target is NOT a register bit: the thread picks entry 0 or 1 from bit `tsel`
-static inline int qcs_op_id_diag_free(int creg) { return 160 + creg + 1; }
-// diagonal whose target is register bit treg; halves: 1 = entry 0 only, 2 = entry 1 only, 3 = both
+// diagonal whose target is NOT a register bit: the thread picks entry 0 or 1 from bit `tsel` of its
+// own basis index; halves: 1 = only entry 0 differs from the identity, 2 = only entry 1, 3 = both
+static inline int qcs_op_id_diag_free(int creg, int halves) { return 160 + (creg + 1) * 3 + (halves - 1); }
+// diagonal whose target is register bit treg; halves as above
 static inline int qcs_op_id_diag_reg(int treg, int creg, int halves) {
-  return 165 + (treg * 5 + creg + 1) * 3 + (halves - 1);
+  return 175 + (treg * 5 + creg + 1) * 3 + (halves - 1);
 }
-#define QCS_OP_DIAG_FREE_FIRST 160
-#define QCS_OP_DIAG_FREE_LAST 164
-#define QCS_OP_NONE 255
-// Header of a controlled-phase fan: the next `tsel` gate records are diag(1, e^{ia}) gates
-// controlled by various qubits on ONE target; `ctest` = selector of the target bit when it is not
-// a register bit (0xFF otherwise), treg in treg_creg.  The interpreter runs them in a tight loop.
-#define QCS_OP_FAN 250
-#define QCS_MAX_PASS_FANS 24
-// DGate.ctest / DGate.tsel: 0..11 = tile-bit index (per-thread test), QCS_SEL_OUTSIDE | pos =
-// physical position outside the tile (same value for the whole tile), 0xFF = none
-#define QCS_SEL_OUTSIDE 0x40
+// Header of a controlled-phase fan, op = QCS_OP_FAN_BASE + treg + 1: the next `tsel` (<= 32) gate
+// records are diag(1, e^{ia}) gates on ONE target (tpos; register role treg, -1 = not a register
+// bit), each controlled by a bit that is NOT a register bit of the segment (so it has one value for
+// all amplitudes of a thread).  csel = control position of the first entry when entry k is
+// controlled by position csel + k (the QFT's shape: a thread's participation mask is one shift of
+// its own basis index), else 0xFF (the mask is gathered from the entries' cpos).  The interpreter
+// walks the entries in a tight loop: one predicate + two constant loads around each FP64 block.
+#define QCS_OP_FAN_BASE 240
+#define QCS_MAX_FAN_ENTRIES 32
+#define QCS_MAX_PASS_FANS 32
+// or-ed into a pairing / diagonal id: the gate's control is a bit the thread tests once for all its
+// amplitudes (a lane / warp tile bit, a position outside the tile, a rank bit); csel = its position
+#define QCS_OP_TCTL 0x100
+#define QCS_OP_NONE 255      // symbolic id of "execute nothing"
 
 // A gate as the device sees it (inside a pass descriptor).  The kernel reads
 // m[] and the first four header bytes; the rest documents the plan.
 struct DGate {
   double m[8];      // row-major {re,im} x 4
-  uint8_t op;       // dispatch id (above)
-  uint8_t flags;    // GateFlags
-  uint8_t ctest;    // control that is not a register bit: selector (QCS_SEL_*) of the bit that must
-                    // be 1 for this thread to take part; 0xFF = no test
-  uint8_t tsel;     // for diag_free ops: selector of the target bit, else 0xFF
+  uint16_t op;      // dispatch id (above)
+  uint8_t csel;     // QCS_OP_TCTL ops: physical position of the control bit; fans: see above; else 0xFF
+  uint8_t tsel;     // diag_free ops: physical position of the target bit; fans: entry count; else 0xFF
   uint8_t kind;     // GateKind
+  uint8_t flags;    // GateFlags
   int8_t tpos;      // physical position of the target bit
   int8_t cpos;      // physical position of the control bit, -1 if none
   uint8_t treg_creg; // (treg + 1) | (creg + 1) << 4
+  uint8_t pad[7];
 };
+
+// gen_fused_lists.py hard-codes this layout (OFF_* / SIZEOF_DGATE)
+static_assert(sizeof(DGate) == 80, "DGate layout is part of the generated interpreter");
+static_assert(__builtin_offsetof(DGate, op) == 64 && __builtin_offsetof(DGate, csel) == 66 &&
+              __builtin_offsetof(DGate, tsel) == 67 && __builtin_offsetof(DGate, tpos) == 70 &&
+              __builtin_offsetof(DGate, cpos) == 71, "DGate layout is part of the generated interpreter");
 
 struct DSegment {
   // role r -> tile bit index; roles 0-4 lane bits, then warp bits, the last reg_bits are register bits
@@ -87,6 +99,7 @@ struct DSegment {
   uint16_t gate_begin, gate_end;
   // Host-precomputed per-thread arithmetic (the kernel would otherwise redo it for every tile):
   uint16_t tb_lut[3][8];               // tile-index bits contributed by thread-id bits [3g, 3g+3)
+  uint64_t gb_lut[3][8];               // the same bits as element offsets inside the shard (physical positions)
   uint16_t toff[QCS_MAX_REG_BITS];     // tile-index offset of each register role bit
   uint16_t stoff[QCS_MAX_REG_BITS];    // the same, XOR-swizzled
 };
@@ -106,9 +119,8 @@ struct PassParams {
   int32_t reg_bits;                    // 4: 256 threads x 16 amplitudes, 3: 512 threads x 8
   int32_t n_tile_runs;
   DTileRun tile_run[12];               // tile number -> element offset of the tile (bit deposit as runs)
-  // element offsets for the global loads (first segment) and stores (last segment)
-  uint64_t gb_lut[2][3][8];            // [first/last][thread-id bit group][value]
+  // element offsets of the register role bits for the global loads (first segment) and stores (last)
   uint64_t goff[2][QCS_MAX_REG_BITS];  // [first/last][register role bit]
   DSegment seg[QCS_MAX_PASS_SEGMENTS];
-  DGate gate[QCS_MAX_PASS_GATES + QCS_MAX_PASS_FANS + 1];  // fan headers; +1: one-ahead prefetch sentinel
+  DGate gate[QCS_MAX_PASS_GATES + QCS_MAX_PASS_FANS];  // gates + fan headers
 };

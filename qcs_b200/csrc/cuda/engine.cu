@@ -280,8 +280,8 @@ static int run_local(Engine &e, const std::vector<PhysGate> &gates, bool record_
       dg.flags = g.c.flags;
       dg.tpos = (int8_t)g.tpos;
       dg.cpos = (int8_t)g.cpos;
-      dg.op = QCS_OP_NONE;
-      dg.ctest = dg.tsel = 0xFF;
+      dg.op = 0;  // the per-gate kernels read kind / flags, not the fused interpreter's case label
+      dg.csel = dg.tsel = 0xFF;
       if (!e.opt.dryrun) CK(launch_simple_gate(e.live, dg, e.nl, e.shard_base, e.stream));
       e.kernel_launches++;
       e.gates_executed++;

@@ -1,20 +1,42 @@
 #!/usr/bin/env python3
-"""Generates fused_lists.inc: register lists and the per-gate dispatch switch of the fused tile kernel.
+"""Generates the gate interpreter of the fused tile kernel.
 
 A thread holds NREG = 2^R amplitudes in named PTX registers qr0.. / qi0..; register index bit
 k is register-role bit k.  A gate pairing across role bit T touches pairs (r, r | 1<<T) with
 bit T of r clear, optionally only those with bit C set (control on a register bit).
 
-For each R in (3, 4) this emits
-  QCS<R>_REGS_ALL(OP)            every register
-  QCS<R>_GATE_SWITCH(op)         `switch (op) { case id: <unrolled PTX ops> break; ... }`
-where the case id is the `op` byte the planner stores in DGate (common.h: qcs_op_id_*), so one
-table-driven branch per gate reaches straight-line FP64 code.
+The interpreter is ONE inline-PTX block per register-file shape: a `brx.idx` jump table indexed by
+the gate's case label, every case a straight-line run of mul.rn / add.rn / sub.rn on the named
+registers (never contracted, the reference's operation order: c_mul then c_add, reference
+src/complex.c:23-57), matrix entries fetched from the pass descriptor in kernel-parameter space by
+`ld.param` right where they are used.  Written as C++ `switch` the same table is lowered by the
+compiler to a compare tree (~35 instructions per gate, profiles/r1_fused_kernel_history.md); the
+jump table costs ~11.  FP64 instructions issue at half rate on sm_100, everything else at full
+rate, so a gate's cost is 2 x (FP64 instructions) + (everything else): the dispatch is paid in
+the same currency as the arithmetic.
 
-Run: python gen_fused_lists.py > fused_lists.inc   (build.py does this when the .inc is stale)
+Outputs
+  gen_fused_lists.py lists > fused_lists.inc   QCS<R>_REGS_ALL(OP), QCS<R>_DISPATCH_ASM
+  gen_fused_lists.py ops   > fused_ops.h       QCS<R>_CASE_LABEL[symbolic id] (planner side)
+(build.py regenerates both when this file is newer.)
+
+Asm operands of QCS<R>_DISPATCH_ASM:  %0 "+r" gate index (advanced past what was executed),
+%1 "l" param-space address of the current DGate, %2 "l" xfull = the thread's basis index with the
+register bits clear (rank bits included).
 """
+import sys
 
 KINDS = ["HSYM", "REAL", "SWAP", "GENERIC"]  # order = kind index in qcs_op_id_pair()
+
+# byte offsets inside DGate (common.h)
+OFF_M = lambda i: 8 * i       # noqa: E731  m[i]
+OFF_W0 = 64                   # op (u16) | csel << 16 | tsel << 24
+OFF_TPOS = 70
+OFF_CPOS = 71
+SIZEOF_DGATE = 80
+
+SYM_NOP = 255
+SYM_TCTL = 0x100
 
 
 def pairs(R, t, c):
@@ -39,72 +61,211 @@ def regs(R, t=-1, tval=0, c=-1):
     return res
 
 
+# ---- PTX snippets -----------------------------------------------------------------------------
+def ld_m(indices):
+    return [f"ld.param.f64 g{i}, [%1+{OFF_M(i)}];" for i in indices]
+
+
+def cmul(xr, xi, gr, gi, v):
+    """x = g * v in the reference's c_mul order: x.r = g.r*v.r - g.i*v.i ; x.i = g.r*v.i + g.i*v.r"""
+    return [f"mul.rn.f64 {xr}, {gr}, qr{v};", f"mul.rn.f64 u0, {gi}, qi{v};", f"sub.rn.f64 {xr}, {xr}, u0;",
+            f"mul.rn.f64 {xi}, {gr}, qi{v};", f"mul.rn.f64 u0, {gi}, qr{v};", f"add.rn.f64 {xi}, {xi}, u0;"]
+
+
+def op_pair(kind, row0, a, b):
+    """a = register with target bit 0, b = target bit 1.  Operation order = c_add(c_mul(g0,v0),
+    c_mul(g1,v1)) (reference src/q_gates.c:140-141); row0 = reference-semantics controlled update."""
+    if kind == "HSYM":  # real, U00==U10=m0, U01=m2, U11=-m2: the four products are shared
+        o = [f"mul.rn.f64 t0, g0, qr{a};", f"mul.rn.f64 t1, g0, qi{a};",
+             f"mul.rn.f64 t2, g2, qr{b};", f"mul.rn.f64 t3, g2, qi{b};",
+             f"add.rn.f64 qr{a}, t0, t2;", f"add.rn.f64 qi{a}, t1, t3;"]
+        if not row0:
+            o += [f"sub.rn.f64 qr{b}, t0, t2;", f"sub.rn.f64 qi{b}, t1, t3;"]
+        return o
+    if kind == "REAL":  # all imaginary parts zero
+        o = [f"mul.rn.f64 t0, g0, qr{a};", f"mul.rn.f64 t1, g0, qi{a};",
+             f"mul.rn.f64 t2, g2, qr{b};", f"mul.rn.f64 t3, g2, qi{b};"]
+        if not row0:
+            o += [f"mul.rn.f64 t4, g4, qr{a};", f"mul.rn.f64 t5, g4, qi{a};",
+                  f"mul.rn.f64 t6, g6, qr{b};", f"mul.rn.f64 t7, g6, qi{b};"]
+        o += [f"add.rn.f64 qr{a}, t0, t2;", f"add.rn.f64 qi{a}, t1, t3;"]
+        if not row0:
+            o += [f"add.rn.f64 qr{b}, t4, t6;", f"add.rn.f64 qi{b}, t5, t7;"]
+        return o
+    if kind == "SWAP":  # exact X: moves only
+        if row0:
+            return [f"mov.f64 qr{a}, qr{b};", f"mov.f64 qi{a}, qi{b};"]
+        return [f"mov.f64 t0, qr{a};", f"mov.f64 t1, qi{a};", f"mov.f64 qr{a}, qr{b};",
+                f"mov.f64 qi{a}, qi{b};", f"mov.f64 qr{b}, t0;", f"mov.f64 qi{b}, t1;"]
+    # GENERIC: the full 28-flop update
+    o = cmul("t0", "t1", "g0", "g1", a) + cmul("t2", "t3", "g2", "g3", b)
+    if not row0:
+        o += cmul("t4", "t5", "g4", "g5", a) + cmul("t6", "t7", "g6", "g7", b)
+    o += [f"add.rn.f64 qr{a}, t0, t2;", f"add.rn.f64 qi{a}, t1, t3;"]
+    if not row0:
+        o += [f"add.rn.f64 qr{b}, t4, t6;", f"add.rn.f64 qi{b}, t5, t7;"]
+    return o
+
+
+def pair_loads(kind, row0):
+    if kind == "HSYM":
+        return ld_m([0, 2])
+    if kind == "REAL":
+        return ld_m([0, 2] if row0 else [0, 2, 4, 6])
+    if kind == "SWAP":
+        return []
+    return ld_m([0, 1, 2, 3] if row0 else range(8))
+
+
+def op_diag(r, er="dr", ei="di"):
+    """amplitude r *= (er, ei), c_mul order"""
+    return [f"mul.rn.f64 t0, {er}, qr{r};", f"mul.rn.f64 t1, {ei}, qi{r};",
+            f"mul.rn.f64 t2, {er}, qi{r};", f"mul.rn.f64 t3, {ei}, qr{r};",
+            f"sub.rn.f64 qr{r}, t0, t1;", f"add.rn.f64 qi{r}, t2, t3;"]
+
+
+def thread_bit_test(field_shift, pred="p"):
+    """pred := bit (header byte at w0 >> field_shift) of xfull is SET"""
+    return [f"bfe.u32 cs, w0, {field_shift}, 8;", "shr.u64 t64, %2, cs;", "and.b64 t64, t64, 1;",
+            f"setp.ne.u64 {pred}, t64, 0;"]
+
+
 def emit(R):
-    out = []
     P = f"QCS{R}"
-    out.append(f"#define {P}_REGS_ALL(OP) " + " ".join(f"OP({r})" for r in regs(R)))
-    lines = [f"#define {P}_GATE_SWITCH(op) \\", "  switch (op) { \\"]
-    # pairing ops: id = ((kind*2 + row0)*4 + treg)*5 + (creg+1)
+    labels = {}          # symbolic id -> case label (consecutive)
+    blocks = []          # (label name, [ptx lines])
+
+    def new_case(sym):
+        labels[sym] = len(labels)
+        return f"C{labels[sym]}"
+
+    def case(sym, body, thread_ctl):
+        # a control that is not a register bit: the same block behind one test of the thread's own
+        # basis index; the TCTL label sits right in front of the plain one and falls through
+        if thread_ctl:
+            blocks.append((new_case(sym | SYM_TCTL), thread_bit_test(16) + ["@!p bra DONE;"]))
+        blocks.append((new_case(sym), body + ["bra DONE;"]))
+
+    # pairing ops: symbolic id = ((kind*2 + row0)*4 + treg)*5 + (creg+1)
     for ki, kind in enumerate(KINDS):
         for row0 in (0, 1):
-            opname = f"OP_{kind}" + ("_R0" if row0 else "")
             for t in range(R):
                 for c in range(-1, R):
                     if c == t:
                         continue
-                    op_id = ((ki * 2 + row0) * 4 + t) * 5 + (c + 1)
-                    body = " ".join(f"{opname}({a},{b})" for a, b in pairs(R, t, c))
-                    lines.append(f"    case {op_id}: {{ QCS_LD_{kind}{'_R0' if row0 else ''} {body} }} break; \\")
-    # diagonal, target not a register bit: id = 160 + (creg+1); (dr,di) chosen by the caller
+                    sym = ((ki * 2 + row0) * 4 + t) * 5 + (c + 1)
+                    body = pair_loads(kind, row0)
+                    for a, b in pairs(R, t, c):
+                        body += op_pair(kind, row0, a, b)
+                    case(sym, body, c < 0)
+    # diagonal, target NOT a register bit: id = 160 + (creg+1)*3 + (halves-1); the thread's own target
+    # bit picks the entry.  halves: 1 = only entry 0 is not the identity, 2 = only entry 1, 3 = both
     for c in range(-1, R):
-        body = " ".join(f"OP_DIAG({r})" for r in regs(R, c=c))
-        lines.append(f"    case {160 + c + 1}: {{ {body} }} break; \\")
-    # diagonal, target = register bit t: id = 165 + (t*5 + creg+1)*3 + (halves-1)
-    #   halves: 1 = entry 0 only (target bit clear), 2 = entry 1 only, 3 = both
+        for halves in (1, 2, 3):
+            sym = 160 + (c + 1) * 3 + (halves - 1)
+            body = thread_bit_test(24)
+            if halves == 3:
+                body += ld_m([0, 1, 6, 7]) + ["selp.f64 dr, g6, g0, p;", "selp.f64 di, g7, g1, p;"]
+            elif halves == 2:
+                body += ["@!p bra DONE;", f"ld.param.f64 dr, [%1+{OFF_M(6)}];", f"ld.param.f64 di, [%1+{OFF_M(7)}];"]
+            else:
+                body += ["@p bra DONE;", f"ld.param.f64 dr, [%1+{OFF_M(0)}];", f"ld.param.f64 di, [%1+{OFF_M(1)}];"]
+            for r in regs(R, c=c):
+                body += op_diag(r)
+            case(sym, body, c < 0)
+    # diagonal, target = register bit t: id = 175 + (t*5 + creg+1)*3 + (halves-1)
     for t in range(R):
         for c in range(-1, R):
             if c == t:
                 continue
             for halves in (1, 2, 3):
-                op_id = 165 + (t * 5 + c + 1) * 3 + (halves - 1)
-                body = ""
+                sym = 175 + (t * 5 + c + 1) * 3 + (halves - 1)
+                body = []
                 if halves & 1:
-                    body += "QCS_LD_DIAG0 " + " ".join(f"OP_DIAG0({r})" for r in regs(R, t, 0, c)) + " "
+                    body += ld_m([0, 1])
+                    for r in regs(R, t, 0, c):
+                        body += op_diag(r, "g0", "g1")
                 if halves & 2:
-                    body += "QCS_LD_DIAG1 " + " ".join(f"OP_DIAG1({r})" for r in regs(R, t, 1, c))
-                lines.append(f"    case {op_id}: {{ {body} }} break; \\")
-    lines.append("    default: break; \\")
-    lines.append("  }")
-    out += lines
-    # controlled-phase fan: K consecutive gates diag(1, e^{i a_k}) controlled by c_k on ONE target.
-    # The target's register role is fixed for the run, so the per-entry work is: fetch the phase,
-    # test / select the control, multiply the registers whose target bit is 1.
-    fan = [f"#define {P}_FAN(treg) \\", "  switch (treg) { \\"]
+                    body += ld_m([6, 7])
+                    for r in regs(R, t, 1, c):
+                        body += op_diag(r, "g6", "g7")
+                case(sym, body, c < 0)
+    # controlled-phase fan (id 240 + treg + 1; header layout: common.h QCS_OP_FAN_BASE): K consecutive
+    # gates diag(1, e^{i a_k}) on ONE target, each controlled by a bit that is not a register bit.
+    # Bit k of `mask` = this thread takes part in entry k.  Entries no lane of the warp takes part in
+    # are skipped without being touched; per entry: isolate the lowest pending bit, test the thread's
+    # own bit, fetch the phase, multiply the registers whose target bit is 1.  Same arithmetic and
+    # the same order per amplitude as gate by gate.
     for t in range(-1, R):
-        fan.append(f"    case {t}: \\")
-        fan.append("      QCS_FAN_LOOP_BEGIN \\")
-        fan.append("      switch (creg) { \\")
-        for c in range(R):
-            if c == t:
-                continue
-            body = " ".join(f"OP_DIAG({r})" for r in (regs(R, t, 1, c) if t >= 0 else regs(R, c=c)))
-            fan.append(f"        case {c}: {{ {body} }} break; \\")
-        body = " ".join(f"OP_DIAG({r})" for r in (regs(R, t, 1) if t >= 0 else regs(R)))
-        fan.append(f"        default: {{ {body} }} break; \\")
-        fan.append("      } \\")
-        fan.append("      QCS_FAN_LOOP_END \\")
-        fan.append("      break; \\")
-    fan.append("    default: break; \\")
-    fan.append("  }")
-    out += fan
-    return out
+        sym = 240 + t + 1
+        n = f"{t + 1}"
+        E = SIZEOF_DGATE  # entries follow the header record
+        body = ["bfe.u32 K, w0, 24, 8;", "bfe.u32 c0, w0, 16, 8;", "setp.eq.u32 p, c0, 255;",
+                f"@p bra FG{n};",
+                "shr.u64 t64, %2, c0;", "cvt.u32.u64 mask, t64;",
+                f"FM{n}:", "bfe.u32 mask, mask, 0, K;"]
+        if t < 0:  # the target is a thread-level bit too: all or none of this thread's amplitudes
+            body += [f"ld.param.u8 cs, [%1+{OFF_TPOS}];", "shr.u64 t64, %2, cs;", "and.b64 t64, t64, 1;",
+                     "setp.eq.u64 p, t64, 0;", "@p mov.u32 mask, 0;"]
+        body += ["redux.sync.or.b32 wm, mask, 0xffffffff;",
+                 f"FL{n}:", "setp.eq.u32 p, wm, 0;", f"@p bra FE{n};",
+                 "neg.s32 low, wm;", "and.b32 low, low, wm;", "xor.b32 wm, wm, low;",
+                 "and.b32 tst, mask, low;", "setp.eq.u32 pa, tst, 0;", f"@pa bra FS{n};",
+                 "bfind.u32 kidx, low;", f"mul.wide.u32 ea, kidx, {E};", "add.u64 ea, ea, %1;",
+                 f"ld.param.f64 dr, [ea+{E + OFF_M(6)}];", f"ld.param.f64 di, [ea+{E + OFF_M(7)}];"]
+        for r in (regs(R, t, 1) if t >= 0 else regs(R)):
+            body += op_diag(r)
+        body += [f"FS{n}:", f"bra FL{n};",
+                 f"FE{n}:", "add.s32 %0, %0, K;", "bra DONE;",
+                 # controls at arbitrary positions: gather the mask from the entries' cpos bytes
+                 f"FG{n}:", "mov.u32 mask, 0;", "mov.u32 kidx, 0;", "mov.u64 ea, %1;",
+                 f"FH{n}:", f"ld.param.u8 cs, [ea+{E + OFF_CPOS}];", "shr.u64 t64, %2, cs;",
+                 "cvt.u32.u64 tst, t64;", "and.b32 tst, tst, 1;", "shl.b32 tst, tst, kidx;",
+                 "or.b32 mask, mask, tst;", f"add.u64 ea, ea, {E};", "add.u32 kidx, kidx, 1;",
+                 "setp.lt.u32 p, kidx, K;", f"@p bra FH{n};", f"bra FM{n};"]
+        blocks.append((new_case(sym), body))
+    blocks.append((new_case(SYM_NOP), ["bra DONE;"]))
+
+    n_cases = len(labels)
+    text = ["{", ".reg .b32 w0, op, cs, c0, K, mask, wm, low, tst, kidx;", ".reg .b64 t64, ea;",
+            ".reg .pred p, pa;", ".reg .f64 g<8>, t<8>, u0, dr, di;",
+            f"ld.param.u32 w0, [%1+{OFF_W0}];", "add.s32 %0, %0, 1;", "and.b32 op, w0, 0xffff;",
+            "TS: .branchtargets " + ", ".join(f"C{i}" for i in range(n_cases)) + ";",
+            "brx.idx op, TS;"]
+    for name, body in blocks:
+        text.append(f"{name}:")
+        text += body
+    text += ["DONE:", "}"]
+    out = [f"#define {P}_REGS_ALL(OP) " + " ".join(f"OP({r})" for r in regs(R)),
+           f"#define {P}_DISPATCH_ASM \\"]
+    for line in text:
+        sep = "\\n" if line.endswith(":") or line in ("{", "}") else "\\n\\t"
+        out.append(f'  "{line}{sep}" \\')
+    out[-1] = out[-1][:-2]
+    table = [labels[SYM_NOP]] * 512  # anything unassigned executes nothing
+    for sym, lab in labels.items():
+        table[sym] = lab
+    return out, table
 
 
 def main():
-    out = ["// GENERATED by gen_fused_lists.py -- do not edit.", "#pragma once", ""]
-    for R in (3, 4):
-        out += emit(R)
-        out.append("")
+    what = sys.argv[1] if len(sys.argv) > 1 else "lists"
+    if what == "lists":
+        out = ["// GENERATED by gen_fused_lists.py -- do not edit.", "#pragma once", ""]
+        for R in (3, 4):
+            out += emit(R)[0]
+            out.append("")
+    else:
+        out = ["// GENERATED by gen_fused_lists.py -- do not edit.",
+               "// symbolic op id (common.h qcs_op_id_*, | QCS_OP_TCTL) -> case label of the generated jump table",
+               "#pragma once", ""]
+        for R in (3, 4):
+            table = emit(R)[1]
+            out.append(f"static const unsigned short QCS{R}_CASE_LABEL[512] = {{")
+            for i in range(0, 512, 16):
+                out.append("  " + ", ".join(str(v) for v in table[i:i + 16]) + ",")
+            out.append("};")
+            out.append("")
     print("\n".join(out))
 
 

@@ -1,6 +1,8 @@
 // planner.cpp -- see planner.h.  Pure host code.
 #include "planner.h"
 
+#include "fused_ops.h"
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -229,15 +231,13 @@ struct PassBuilder {
     }
     pp.n_segments = (int)segs.size();
     pp.reg_bits = cfg.reg_bits;
-    // A bit that is not a register bit is tested once per thread (lane / warp tile
-    // bits: encoded as the tile-bit index) or once per tile (positions outside the
-    // tile: QCS_SEL_OUTSIDE | physical position).
-    auto encode_sel = [&](int pos, int tilebit) -> uint8_t {
-      return tilebit >= 0 ? (uint8_t)tilebit : (uint8_t)(QCS_SEL_OUTSIDE | pos);
-    };
     auto is_cphase = [](const PhysGate &g) {
       return g.c.kind == GK_DIAG && g.cpos >= 0 && (g.c.flags & GF_D0_IDENT) &&
              !(g.c.flags & GF_D1_IDENT);
+    };
+    // symbolic op id -> case label of the generated switch for this register-file shape
+    auto case_label = [&](int sym) -> uint16_t {
+      return cfg.reg_bits == 3 ? QCS3_CASE_LABEL[sym] : QCS4_CASE_LABEL[sym];
     };
     int out_n = 0, n_fans = 0, fan_left = 0;
     for (int si = 0; si < (int)segs.size(); si++) {
@@ -253,24 +253,29 @@ struct PassBuilder {
       for (int gi = segs[si].begin; gi < segs[si].end; gi++) {
         const PhysGate &g = gates[gi];
         const int treg = reg_of(g.tpos), creg = reg_of(g.cpos);
-        const int tb = tilebit_of(g.tpos);
-        const int cb = g.cpos >= 0 ? tilebit_of(g.cpos) : -1;
-        // Controlled-phase fan: a run of >= 3 consecutive controlled diag(1, e^{ia}) gates on one
-        // target gets a header so the kernel walks it in a tight loop (QFT: one fan per round).
-        if (is_cphase(g) && n_fans < QCS_MAX_PASS_FANS) {
+        // Controlled-phase fan: a run of consecutive controlled diag(1, e^{ia}) gates on one target
+        // whose controls are not register bits gets a header so the kernel walks it in a tight
+        // loop (QFT: one or two fans per round).  Entries controlled by a register bit stay
+        // ordinary gates and split the run.
+        auto fan_entry = [&](const PhysGate &x) { return is_cphase(x) && reg_of(x.cpos) < 0; };
+        if (fan_left == 0 && fan_entry(g) && n_fans < QCS_MAX_PASS_FANS) {
           int run = 1;
-          while (gi + run < segs[si].end && is_cphase(gates[gi + run]) &&
-                 gates[gi + run].tpos == g.tpos && run < 120)
+          bool consecutive = true;
+          while (gi + run < segs[si].end && fan_entry(gates[gi + run]) &&
+                 gates[gi + run].tpos == g.tpos && run < QCS_MAX_FAN_ENTRIES) {
+            if (gates[gi + run].cpos != g.cpos + run) consecutive = false;
             run++;
-          if (run >= 3 && fan_left == 0) {
+          }
+          if (run >= 2) {
             DGate &hd = pp.gate[out_n++];
             std::memset(&hd, 0, sizeof(hd));
-            hd.op = QCS_OP_FAN;
+            hd.op = case_label(QCS_OP_FAN_BASE + treg + 1);
             hd.kind = GK_DIAG;
+            hd.flags = GF_FAN_HEADER;
+            hd.csel = consecutive ? (uint8_t)g.cpos : 0xFF;
             hd.tsel = (uint8_t)run;  // number of entries that follow
-            hd.ctest = treg < 0 ? encode_sel(g.tpos, tb) : 0xFF;
             hd.tpos = (int8_t)g.tpos;
-            hd.cpos = -1;
+            hd.cpos = (int8_t)g.cpos;
             hd.treg_creg = (uint8_t)(treg + 1);
             n_fans++;
             fan_left = run;
@@ -278,31 +283,39 @@ struct PassBuilder {
         }
         if (fan_left > 0) fan_left--;
         DGate &dg = pp.gate[out_n++];
+        std::memset(&dg, 0, sizeof(dg));
         std::memcpy(dg.m, g.c.m, sizeof(dg.m));
         dg.kind = g.c.kind;
         dg.flags = g.c.flags;
         dg.tpos = (int8_t)g.tpos;
         dg.cpos = (int8_t)g.cpos;
         dg.treg_creg = (uint8_t)((treg + 1) | ((creg + 1) << 4));
-        dg.ctest = (g.cpos >= 0 && creg < 0) ? encode_sel(g.cpos, cb) : 0xFF;
+        // a control that is not a register bit is tested once per thread on its own basis index
+        const bool thread_ctl = g.cpos >= 0 && creg < 0;
+        dg.csel = thread_ctl ? (uint8_t)g.cpos : 0xFF;
         dg.tsel = 0xFF;
         const int row0 = (g.c.flags & GF_ROW0_ONLY) ? 1 : 0;
+        int op = QCS_OP_NONE;
         switch (g.c.kind) {
-          case GK_PAIR_HSYM: dg.op = (uint8_t)qcs_op_id_pair(0, row0, treg, creg); break;
-          case GK_PAIR_REAL: dg.op = (uint8_t)qcs_op_id_pair(1, row0, treg, creg); break;
-          case GK_PAIR_SWAP: dg.op = (uint8_t)qcs_op_id_pair(2, row0, treg, creg); break;
-          case GK_PAIR_GENERIC: dg.op = (uint8_t)qcs_op_id_pair(3, row0, treg, creg); break;
-          case GK_DIAG:
+          case GK_PAIR_HSYM: op = qcs_op_id_pair(0, row0, treg, creg); break;
+          case GK_PAIR_REAL: op = qcs_op_id_pair(1, row0, treg, creg); break;
+          case GK_PAIR_SWAP: op = qcs_op_id_pair(2, row0, treg, creg); break;
+          case GK_PAIR_GENERIC: op = qcs_op_id_pair(3, row0, treg, creg); break;
+          case GK_DIAG: {
+            const int halves = ((g.c.flags & GF_D0_IDENT) ? 0 : 1) | ((g.c.flags & GF_D1_IDENT) ? 0 : 2);
+            if (!halves) break;
             if (treg < 0) {
-              dg.op = (uint8_t)qcs_op_id_diag_free(creg);
-              dg.tsel = encode_sel(g.tpos, tb);
+              op = qcs_op_id_diag_free(creg, halves);
+              dg.tsel = (uint8_t)g.tpos;
             } else {
-              const int halves = ((g.c.flags & GF_D0_IDENT) ? 0 : 1) | ((g.c.flags & GF_D1_IDENT) ? 0 : 2);
-              dg.op = halves ? (uint8_t)qcs_op_id_diag_reg(treg, creg, halves) : (uint8_t)QCS_OP_NONE;
+              op = qcs_op_id_diag_reg(treg, creg, halves);
             }
             break;
-          default: dg.op = QCS_OP_NONE; break;
+          }
+          default: break;
         }
+        if (op != QCS_OP_NONE && thread_ctl) op |= QCS_OP_TCTL;
+        dg.op = case_label(op);
       }
       ds.gate_end = (uint16_t)out_n;
     }
@@ -328,15 +341,18 @@ struct PassBuilder {
         ds.stoff[k] = (uint16_t)swz(off);
       }
     }
-    for (int which = 0; which < 2; which++) {
-      const DSegment &ds = pp.seg[which == 0 ? 0 : (int)segs.size() - 1];
+    for (int si = 0; si < (int)segs.size(); si++) {
+      DSegment &ds = pp.seg[si];
       for (int g = 0; g < 3; g++)
         for (int v = 0; v < 8; v++) {
           uint64_t off = 0;
           for (int b = 0; b < QCS_TILE_BITS; b++)
             if ((ds.tb_lut[g][v] >> b) & 1) off |= 1ull << pp.tile_pos[b];
-          pp.gb_lut[which][g][v] = off;
+          ds.gb_lut[g][v] = off;
         }
+    }
+    for (int which = 0; which < 2; which++) {
+      const DSegment &ds = pp.seg[which == 0 ? 0 : (int)segs.size() - 1];
       for (int k = 0; k < cfg.reg_bits; k++)
         pp.goff[which][k] = 1ull << pp.tile_pos[ds.role_tilebit[thread_roles + k]];
     }
@@ -355,11 +371,6 @@ struct PassBuilder {
       }
       pp.n_tile_runs = n_runs;  // <= 8: seven tile bits above position 4 split the rest into <= 8 runs
     }
-    // sentinel header read by the interpreter's one-ahead prefetch
-    std::memset(&pp.gate[out_n], 0, sizeof(DGate));
-    pp.gate[out_n].op = QCS_OP_NONE;
-    pp.gate[out_n].ctest = 0xFF;
-    pp.gate[out_n].tsel = 0xFF;
     plan.n_gates_api = n_api;
     plan.flops_per_amp = flops;
     return plan;
@@ -415,7 +426,7 @@ std::string describe_plan(const std::vector<PassPlan> &passes) {
       s += buf;
       for (int gi = ds.gate_begin; gi < ds.gate_end; gi++) {
         const DGate &g = pp.gate[gi];
-        if (g.op == QCS_OP_FAN) {
+        if (g.flags & GF_FAN_HEADER) {
           std::snprintf(buf, sizeof(buf), " fan[%d]", (int)g.tsel);
           s += buf;
           continue;
