@@ -19,7 +19,7 @@
 #define QCS_TILE_BITS 12     // 4096 amplitudes = 64 KiB per tile
 #define QCS_LANE_BITS 5
 #define QCS_MAX_REG_BITS 4   // 16 amplitudes per thread (256-thread CTA) or 8 (512-thread CTA)
-#define QCS_MAX_PASS_GATES 120
+#define QCS_MAX_PASS_GATES 240
 #define QCS_MAX_PASS_SEGMENTS 12
 
 // Arithmetic classes.  Every class performs the reference's operations in the
@@ -66,7 +66,7 @@ static inline int qcs_op_id_diag_reg(int treg, int creg, int halves) {
 // walks the entries in a tight loop: one predicate + two constant loads around each FP64 block.
 #define QCS_OP_FAN_BASE 240
 #define QCS_MAX_FAN_ENTRIES 32
-#define QCS_MAX_PASS_FANS 32
+#define QCS_MAX_PASS_FANS 48
 // or-ed into a pairing / diagonal id: the gate's control is a bit the thread tests once for all its
 // amplitudes (a lane / warp tile bit, a position outside the tile, a rank bit); csel = its position
 #define QCS_OP_TCTL 0x100

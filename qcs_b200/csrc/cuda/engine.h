@@ -17,7 +17,7 @@ struct Options {
   Semantics sem = SEM_REFERENCE;
   bool fusion = true;
   bool dryrun = false;
-  double pass_flops = 200.0;  // FP64 work per amplitude a pass may fuse (measured optimum: scripts/budget_sweep.py)
+  double pass_flops = 1000.0;  // FP64 work per amplitude a pass may fuse; measured flat above ~200 (scripts/budget_sweep.py): a pass costs max(memory, FP64), splitting it never helps
   int exchange = 0;  // 0: NCCL send/recv, 1: peer-memory swap kernel
   int tile_kernel = 3;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8), 3: ldg8 (512 thr x 8 amps, plain loads; default)
 };

@@ -73,40 +73,78 @@ static bool is_pairing(uint8_t kind) {
          kind == GK_PAIR_SWAP;
 }
 
-// Assigns the 12 tile bits to roles for one segment.  `regbits` (tile-bit
-// indices) become the register roles; of the rest, three bits with distinct
-// residues mod 3 become lane bits 0..2 so that, with the XOR swizzle used by
-// the kernel (slot ^ (slot>>3) ^ (slot>>6) ^ (slot>>9) on the low 3 bits),
-// every quarter-warp of a 16-byte shared-memory access hits 8 distinct bank
-// groups.  With no register bit below 5 this yields lane bits = tile bits
-// 0..4, i.e. fully coalesced 512-byte global rows per warp.
-static void assign_roles(const std::vector<int> &regbits, uint8_t role_tilebit[QCS_TILE_BITS]) {
+// Assigns the 12 tile bits to roles for one segment.  `regbits` (tile-bit indices) become the
+// register roles.  Five of the rest become lane bits: a gate whose control (or diagonal target) is
+// a lane bit runs with half of the warp idle, so the five bits with the least such work
+// (`lane_cost`, flops per amplitude) are chosen; among equals the lowest bits win, which gives
+// lane bits = tile bits 0..4 = fully coalesced 512-byte global rows per warp, and `force_low`
+// demands exactly that (first / last segment of a pass).  Lane roles 0..2 get three bits with
+// distinct residues mod 3 when possible so that, with the XOR swizzle used by the kernel
+// (slot ^ (slot>>3) ^ (slot>>6) ^ (slot>>9) on the low 3 bits), every quarter-warp of a 16-byte
+// shared-memory access hits 8 distinct bank groups.  Returns the lane cost of the choice.
+static double assign_roles(const std::vector<int> &regbits, const double lane_cost[QCS_TILE_BITS],
+                           bool force_low, uint8_t role_tilebit[QCS_TILE_BITS]) {
   bool is_reg[QCS_TILE_BITS] = {false};
   for (int b : regbits) is_reg[b] = true;
   std::vector<int> rest;
   for (int b = 0; b < QCS_TILE_BITS; b++)
     if (!is_reg[b]) rest.push_back(b);
+  const int n = (int)rest.size();
+  auto residues_ok = [&](unsigned subset) {
+    bool r[3] = {false, false, false};
+    for (int i = 0; i < n; i++)
+      if ((subset >> i) & 1u) r[rest[i] % 3] = true;
+    return r[0] && r[1] && r[2];
+  };
+  unsigned best = 0;
+  double best_cost = 0.0;
+  int best_bad = 0, best_sum = 0;
+  bool have = false;
+  for (unsigned subset = 0; subset < (1u << n); subset++) {
+    if (__builtin_popcount(subset) != QCS_LANE_BITS) continue;
+    double cost = 0.0;
+    int sum = 0;
+    bool low_only = true;
+    for (int i = 0; i < n; i++)
+      if ((subset >> i) & 1u) {
+        cost += lane_cost[rest[i]];
+        sum += rest[i];
+        if (rest[i] >= QCS_LANE_BITS) low_only = false;
+      }
+    if (force_low && !low_only) continue;
+    const int bad = residues_ok(subset) ? 0 : 1;
+    if (!have || cost < best_cost - 1e-9 ||
+        (cost < best_cost + 1e-9 && (bad < best_bad || (bad == best_bad && sum < best_sum)))) {
+      have = true;
+      best = subset;
+      best_cost = cost;
+      best_bad = bad;
+      best_sum = sum;
+    }
+  }
+  if (!have) return assign_roles(regbits, lane_cost, false, role_tilebit);  // a register bit below 5
+  std::vector<int> lanes, warps;
+  for (int i = 0; i < n; i++) (((best >> i) & 1u) ? lanes : warps).push_back(rest[i]);
   std::vector<int> lane_lo;
-  bool used_res[3] = {false, false, false};
-  bool taken[QCS_TILE_BITS] = {false};
-  for (int b : rest) {
+  bool used_res[3] = {false, false, false}, taken[QCS_TILE_BITS] = {false};
+  for (int b : lanes)
     if ((int)lane_lo.size() < 3 && !used_res[b % 3]) {
       lane_lo.push_back(b);
       used_res[b % 3] = true;
       taken[b] = true;
     }
-  }
-  for (int b : rest) {
+  for (int b : lanes)
     if ((int)lane_lo.size() < 3 && !taken[b]) {
       lane_lo.push_back(b);
       taken[b] = true;
     }
-  }
   int role = 0;
   for (int b : lane_lo) role_tilebit[role++] = (uint8_t)b;
-  for (int b : rest)
-    if (!taken[b]) role_tilebit[role++] = (uint8_t)b;  // lane 3,4 then warp 0..2
+  for (int b : lanes)
+    if (!taken[b]) role_tilebit[role++] = (uint8_t)b;          // lane roles 3, 4
+  for (int b : warps) role_tilebit[role++] = (uint8_t)b;      // warp roles
   for (int b : regbits) role_tilebit[role++] = (uint8_t)b;
+  return best_cost;
 }
 
 namespace {
@@ -215,16 +253,43 @@ struct PassBuilder {
         if (std::find(s.regbits.begin(), s.regbits.end(), b) == s.regbits.end())
           s.regbits.push_back(b);
     }
+    // Work a tile bit would waste as a lane bit of segment s: gates that test it once per thread
+    // (a control or a diagonal target that is not a register bit) run with half the warp idle.
+    auto lane_costs = [&](const Seg &s, double cost[QCS_TILE_BITS]) {
+      for (int b = 0; b < QCS_TILE_BITS; b++) cost[b] = 0.0;
+      auto is_reg = [&](int tb) {
+        return std::find(s.regbits.begin(), s.regbits.end(), tb) != s.regbits.end();
+      };
+      for (int gi = s.begin; gi < s.end; gi++) {
+        const PhysGate &g = gates[gi];
+        const int cb = g.cpos >= 0 ? tilebit_of(g.cpos) : -1;
+        if (cb >= 0 && !is_reg(cb)) cost[cb] += g.c.flops_per_amp;
+        const int tb = tilebit_of(g.tpos);
+        if (g.c.kind == GK_DIAG && tb >= 0 && !is_reg(tb)) cost[tb] += g.c.flops_per_amp;
+      }
+    };
+    // The first and the last segment load / store global memory with their lane bits as the fastest
+    // index, so they must keep tile bits 0..4 on the lanes.  Where that is impossible (a register
+    // bit below 5) or wasteful (low bits busy as controls / diagonal targets), a gate-less segment
+    // is added for the I/O and the gates get the lanes that suit them: one more transposition
+    // through shared memory, worth about kSegmentCost flops per amplitude.
+    const double kSegmentCost = 6.0;
     if (cfg.direct_io) {
-      auto low = [](const Seg &s) {
+      auto wants_own_io = [&](const Seg &s) {
         for (int b : s.regbits)
           if (b < QCS_LANE_BITS) return true;
-        return false;
+        if ((int)segs.size() + 2 > QCS_MAX_PASS_SEGMENTS) return false;
+        double cost[QCS_TILE_BITS];
+        uint8_t scratch[QCS_TILE_BITS];
+        lane_costs(s, cost);
+        return assign_roles(s.regbits, cost, true, scratch) >
+               assign_roles(s.regbits, cost, false, scratch) + kSegmentCost;
       };
       std::vector<int> io_regs;
       for (int k = cfg.reg_bits; k >= 1; k--) io_regs.push_back(QCS_TILE_BITS - k);
-      if (low(segs.front())) segs.insert(segs.begin(), Seg{io_regs, 0, 0});
-      if (low(segs.back())) {
+      const bool front = wants_own_io(segs.front()), back = wants_own_io(segs.back());
+      if (front) segs.insert(segs.begin(), Seg{io_regs, 0, 0});
+      if (back) {
         int e = (int)gates.size();
         segs.push_back(Seg{io_regs, e, e});
       }
@@ -242,7 +307,12 @@ struct PassBuilder {
     int out_n = 0, n_fans = 0, fan_left = 0;
     for (int si = 0; si < (int)segs.size(); si++) {
       DSegment &ds = pp.seg[si];
-      assign_roles(segs[si].regbits, ds.role_tilebit);
+      {
+        double cost[QCS_TILE_BITS];
+        lane_costs(segs[si], cost);
+        const bool io = cfg.direct_io && (si == 0 || si == (int)segs.size() - 1);
+        assign_roles(segs[si].regbits, cost, io, ds.role_tilebit);
+      }
       ds.gate_begin = (uint16_t)out_n;
       auto reg_of = [&](int pos) -> int {
         const int tbit = pos >= 0 ? tilebit_of(pos) : -1;

@@ -88,8 +88,8 @@ def test_qft30_plan_is_compact():
     text, st = _plan(30, [("qft",)], semantics="corrected")
     passes = _parse(text)
     assert st["gates_submitted"] == 465
-    assert len(passes) <= 8, len(passes)
-    assert all(p["flops"] <= 210 for p in passes)   # default budget: 200 flops per amplitude per pass
+    assert len(passes) <= 5, len(passes)            # 30 pairing targets, 12 then 7 new positions per pass
+    assert all(p["api"] <= 240 for p in passes)     # QCS_MAX_PASS_GATES
 
 
 def test_reference_semantics_cphase_is_a_value_noop():
