@@ -101,7 +101,8 @@ int qcs_cuda_write_amplitudes(qcs_cuda_engine *e, int which, long first,
 /* ---- configuration / introspection ------------------------------------------------ */
 /* Keys: "semantics" = reference|corrected, "fusion" = on|off,
  * "dryrun" = 0|1, "pass_flops" = <float>, "tile_kernel" = ldg8|ldg|tma|tma16,
- * "exchange" = p2p|nccl (multi-GPU position swaps: in-place peer-memory kernel, or NCCL send/recv).
+ * "exchange" = p2p|nccl (multi-GPU position swaps: in-place peer-memory kernel, or NCCL send/recv),
+ * "fuse_swaps" = on|off (p2p only: a swap rides on the stores of a fused pass instead of a kernel of its own).
  * Defaults come from QCS_CUDA_<KEY> in the environment; set_default applies
  * to engines created afterwards. */
 int qcs_cuda_set_default(const char *key, const char *value);
@@ -121,7 +122,10 @@ typedef struct qcs_cuda_stats {
   double pass_bytes;           /* same, fused tile passes only               */
   double pass_ms;              /* device time inside fused tile passes       */
   double exchange_bytes;       /* bytes sent over NVLink by this rank        */
-  double exchange_ms;          /* device time inside exchanges               */
+  double exchange_ms;          /* device time inside stand-alone exchanges   */
+  long fused_remaps;           /* remaps folded into the stores of a pass    */
+  double fused_remap_pass_ms;  /* device time of the passes that carried one
+                                  (also counted in pass_ms)                  */
 } qcs_cuda_stats;
 
 int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out);

@@ -29,6 +29,7 @@ class Stats(ctypes.Structure):
         ("kernel_launches", _L), ("segments", _L), ("remaps", _L),
         ("algorithmic_bytes", _D), ("pass_bytes", _D), ("pass_ms", _D),
         ("exchange_bytes", _D), ("exchange_ms", _D),
+        ("fused_remaps", ctypes.c_long), ("fused_remap_pass_ms", _D),
     ]
 
     def as_dict(self) -> dict:

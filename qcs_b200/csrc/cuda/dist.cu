@@ -110,30 +110,17 @@ unpack_half_kernel(double2 *__restrict__ live, const double2 *__restrict__ stagi
   }
 }
 
-// same descriptor as kernels_fused.cu slice_expand, here in pair-index space
-__device__ __forceinline__ uint64_t slice_expand_pairs(uint64_t dense, uint64_t desc) {
-  const uint32_t count = (uint32_t)(desc >> 24) & 0xffu;
-  const uint32_t value = (uint32_t)(desc >> 32);
-  for (uint32_t b = 0; b < count; b++) {
-    const uint32_t pos = (uint32_t)(desc >> (8 * b)) & 0xffu;
-    const uint64_t low = dense & ((1ull << pos) - 1ull);
-    dense = ((dense >> pos) << (pos + 1)) | low | ((uint64_t)((value >> b) & 1u) << pos);
-  }
-  return dense;
-}
-
 // In-place position swap over NVLink peer memory: pair j = (my element with bit lpos ==
 // `leaving`, the partner's element with the opposite bit).  Each rank handles half of the pairs
 // (`share`), reading one side remotely and writing one side remotely, so both directions of the
 // link carry 8 * 2^nl bytes -- the minimum -- and no staging buffer or pack/unpack pass exists.
 __global__ void __launch_bounds__(256)
 p2p_swap_kernel(double2 *__restrict__ mine, double2 *__restrict__ peer, uint64_t pairs_begin,
-                uint64_t pairs_end, int pos, uint64_t leaving, uint64_t slice) {
+                uint64_t pairs_end, int pos, uint64_t leaving) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t bit = 1ull << pos;
-  for (uint64_t m = pairs_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < pairs_end;
-       m += stride) {
-    const uint64_t j = slice_expand_pairs(m, slice);  // dense index inside the slice -> pair index
+  for (uint64_t j = pairs_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < pairs_end;
+       j += stride) {
     const uint64_t low = j & (bit - 1ull);
     const uint64_t i = (((j >> pos) << (pos + 1)) | low) | (leaving << pos);
     const uint64_t ip = i ^ bit;
@@ -146,29 +133,43 @@ p2p_swap_kernel(double2 *__restrict__ mine, double2 *__restrict__ peer, uint64_t
 
 }  // namespace
 
-// Exchanges CUDA IPC handles of every rank's state buffer so that partners can address it.
+// Exchanges CUDA IPC handles of every rank's state buffer and tile-flag array so that partners
+// can address them.
 int dist_open_peers(Engine &e) {
   DistContext &d = dist();
   if (!d.active || e.opt.dryrun) return QCS_CUDA_OK;
-  cudaIpcMemHandle_t mine;
-  CK(cudaIpcGetMemHandle(&mine, e.live));
-  std::vector<cudaIpcMemHandle_t> all(d.world);
+  const size_t n_tiles = e.nl >= QCS_TILE_BITS ? (size_t)1 << (e.nl - QCS_TILE_BITS) : 0;
+  if (n_tiles) {
+    CK(cudaMalloc(&e.tile_flags, n_tiles * sizeof(uint32_t)));
+    CK(cudaMemset(e.tile_flags, 0, n_tiles * sizeof(uint32_t)));
+  }
+  struct Handles { cudaIpcMemHandle_t live, flags; } mine;
+  std::memset(&mine, 0, sizeof(mine));
+  CK(cudaIpcGetMemHandle(&mine.live, e.live));
+  if (e.tile_flags) CK(cudaIpcGetMemHandle(&mine.flags, e.tile_flags));
+  std::vector<Handles> all(d.world);
   int rc = dist_allgather_host(&mine, all.data(), sizeof(mine));
   if (rc) return rc;
   e.peer_live.assign(d.world, nullptr);
+  e.peer_flags.assign(d.world, nullptr);
   for (int r = 0; r < d.world; r++) {
     if (r == d.rank) {
       e.peer_live[r] = e.live;
+      e.peer_flags[r] = e.tile_flags;
       continue;
     }
-    void *ptr = nullptr;
-    cudaError_t ce = cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess);
+    void *ptr = nullptr, *fptr = nullptr;
+    cudaError_t ce = cudaIpcOpenMemHandle(&ptr, all[r].live, cudaIpcMemLazyEnablePeerAccess);
+    if (ce == cudaSuccess && e.tile_flags)
+      ce = cudaIpcOpenMemHandle(&fptr, all[r].flags, cudaIpcMemLazyEnablePeerAccess);
     if (ce != cudaSuccess) {
       cudaGetLastError();
       e.peer_live.clear();  // no peer access: the NCCL path stays in charge
+      e.peer_flags.clear();
       return QCS_CUDA_OK;
     }
     e.peer_live[r] = (double2 *)ptr;
+    e.peer_flags[r] = (uint32_t *)fptr;
   }
   return QCS_CUDA_OK;
 }
@@ -177,7 +178,12 @@ void dist_close_peers(Engine &e) {
   DistContext &d = dist();
   for (int r = 0; r < (int)e.peer_live.size(); r++)
     if (r != d.rank && e.peer_live[r]) cudaIpcCloseMemHandle(e.peer_live[r]);
+  for (int r = 0; r < (int)e.peer_flags.size(); r++)
+    if (r != d.rank && e.peer_flags[r]) cudaIpcCloseMemHandle(e.peer_flags[r]);
   e.peer_live.clear();
+  e.peer_flags.clear();
+  if (e.tile_flags) cudaFree(e.tile_flags);
+  e.tile_flags = nullptr;
 }
 
 static int stream_barrier(Engine &e, cudaStream_t stream) {
@@ -193,15 +199,35 @@ bool dist_p2p_available(const Engine &e) {
   return dist().active && e.opt.exchange == 1 && e.opt.sem == SEM_CORRECTED && !e.peer_live.empty();
 }
 
-// One slice of an in-place position swap on `stream` (slice = 0: the whole shard).  The slice
-// descriptor lives in pair-index space (the local index with bit lpos removed).
-int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos, uint64_t slice) {
+// A position swap folded into the stores of a fused pass (kernels.h SwapStore): fills in the
+// partner's addresses.  False when the peer-memory path is not available.
+bool dist_fused_swap_args(Engine &e, int lpos, int gpos, SwapStore &sw) {
+  if (!dist_p2p_available(e) || !e.tile_flags) return false;
+  DistContext &d = dist();
+  const int gbit = gpos - e.nl;
+  const int partner = d.rank ^ (1 << gbit);
+  if (!e.peer_flags[partner]) return false;
+  sw.peer = e.peer_live[partner];
+  sw.my_flags = e.tile_flags;
+  sw.peer_flags = e.peer_flags[partner];
+  sw.epoch = ++e.swap_epoch;
+  sw.lpos = (uint32_t)lpos;
+  sw.my_gbit = (uint32_t)((d.rank >> gbit) & 1);
+  sw.lpos_in_tile = 0;  // the caller knows the pass's tile
+  return true;
+}
+
+// After a pass that stored into the partner's shard: nobody reads swapped data before both
+// ranks' kernels (hence their remote stores) have completed.
+int dist_after_fused_swap(Engine &e) { return stream_barrier(e, e.stream); }
+
+// In-place position swap on `stream`.
+int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos) {
   DistContext &d = dist();
   const int gbit = gpos - e.nl;
   const int partner = d.rank ^ (1 << gbit);
   const uint64_t mybit = (uint64_t)((d.rank >> gbit) & 1);
-  const unsigned slice_bits = (unsigned)(slice >> 24) & 0xffu;
-  const uint64_t n_pairs = (e.local_size >> 1) >> slice_bits;
+  const uint64_t n_pairs = e.local_size >> 1;
   const uint64_t begin = mybit ? n_pairs / 2 : 0, end = mybit ? n_pairs : n_pairs / 2;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (e.timing) {
@@ -211,9 +237,8 @@ int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos, uint64_t s
   }
   int rc = stream_barrier(e, stream);  // the partner finished its previous work on these elements
   if (rc) return rc;
-  const unsigned blocks = slice_bits ? 148 * 8 : 148 * 16;
-  p2p_swap_kernel<<<blocks, 256, 0, stream>>>(e.live, e.peer_live[partner], begin, end, lpos,
-                                              1ull - mybit, slice);
+  p2p_swap_kernel<<<148 * 16, 256, 0, stream>>>(e.live, e.peer_live[partner], begin, end, lpos,
+                                                1ull - mybit);
   CK(cudaGetLastError());
   e.kernel_launches++;
   rc = stream_barrier(e, stream);      // nobody reads swapped data before both halves of the pairs are done
@@ -228,7 +253,7 @@ int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos, uint64_t s
 int dist_swap_positions(Engine &e, int lpos, int gpos) {
   DistContext &d = dist();
   if (!d.active) return set_error(QCS_CUDA_ERR_INVALID, "global position without a communicator");
-  if (dist_p2p_available(e)) return dist_p2p_swap(e, e.stream, lpos, gpos, 0);
+  if (dist_p2p_available(e)) return dist_p2p_swap(e, e.stream, lpos, gpos);
   ncclComm_t comm = (ncclComm_t)d.comm;
   const int gbit = gpos - e.nl;
   const int partner = d.rank ^ (1 << gbit);

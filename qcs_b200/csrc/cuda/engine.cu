@@ -84,6 +84,8 @@ static int load_options(Options &o) {
   if (v == "nccl") o.exchange = 0;
   else if (v.empty() || v == "p2p") o.exchange = 1;
   else return set_error(QCS_CUDA_ERR_INVALID, "exchange must be p2p|nccl, got '%s'", v.c_str());
+  v = option_value("fuse_swaps");
+  o.fuse_swaps = !(v == "off" || v == "0");
   return QCS_CUDA_OK;
 }
 
@@ -163,7 +165,7 @@ static cudaEvent_t get_event(Engine &e) {
 }
 
 static void fold_events(Engine &e) {
-  if (e.pending_pass_events.empty() && e.pending_xchg_events.empty()) return;
+  if (e.pending_pass_events.empty() && e.pending_xchg_events.empty() && e.pending_fused_events.empty()) return;
   cudaStreamSynchronize(e.stream);
   for (auto &pr : e.pending_pass_events) {
     float ms = 0.f;
@@ -179,6 +181,16 @@ static void fold_events(Engine &e) {
     e.event_pool.push_back(pr.second);
   }
   e.pending_xchg_events.clear();
+  for (auto &pr : e.pending_fused_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+      e.fused_swap_pass_ms += ms;
+      e.pass_ms += ms;
+    }
+    e.event_pool.push_back(pr.first);
+    e.event_pool.push_back(pr.second);
+  }
+  e.pending_fused_events.clear();
 }
 
 // ------------------------------------------------------------------ scratch buffer
@@ -219,57 +231,87 @@ static double gate_bytes(const Engine &e, const PhysGate &g) {
   return 32.0 * amps * frac;
 }
 
-// Runs a list of physical gates whose pairing targets are all local.
-static int run_local(Engine &e, const std::vector<PhysGate> &gates, bool record_plan) {
-  if (gates.empty()) return QCS_CUDA_OK;
-  if (e.opt.dryrun) {
-    for (const PhysGate &g : gates) {
-      Engine::TraceEntry t{};
-      t.v[0] = 1.0;
-      t.v[1] = (double)(g.c.kind | (g.c.flags << 8));
-      t.v[2] = (double)g.tpos;
-      t.v[3] = (double)g.cpos;
-      for (int k = 0; k < 8; k++) t.v[4 + k] = g.c.m[k];
-      e.trace.push_back(t);
-    }
+static void trace_gates(Engine &e, const std::vector<PhysGate> &gates) {
+  for (const PhysGate &g : gates) {
+    Engine::TraceEntry t{};
+    t.v[0] = 1.0;
+    t.v[1] = (double)(g.c.kind | (g.c.flags << 8));
+    t.v[2] = (double)g.tpos;
+    t.v[3] = (double)g.cpos;
+    for (int k = 0; k < 8; k++) t.v[4 + k] = g.c.m[k];
+    e.trace.push_back(t);
   }
-  const bool fused = e.opt.fusion && e.nl >= QCS_TILE_BITS;
-  if (fused) {
-    PlannerConfig cfg;
-    cfg.n_local = e.nl;
-    cfg.rank_bits = e.n - e.nl;
-    cfg.shard_base = e.shard_base;
-    cfg.sem = e.opt.sem;
-    cfg.pass_flops_budget = e.opt.pass_flops;
-    cfg.direct_io = true;
-    cfg.reg_bits = (e.opt.tile_kernel >= 2) ? 3 : 4;
-    std::vector<PassPlan> plan = plan_passes(gates, cfg);
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (e.timing && !e.opt.dryrun && !plan.empty()) {
-      ev0 = get_event(e);
-      ev1 = get_event(e);
-      cudaEventRecord(ev0, e.stream);
-    }
-    for (const PassPlan &p : plan) {
-      if (!e.opt.dryrun) {
+}
+
+static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysGate> &gates) {
+  PlannerConfig cfg;
+  cfg.n_local = e.nl;
+  cfg.rank_bits = e.n - e.nl;
+  cfg.shard_base = e.shard_base;
+  cfg.sem = e.opt.sem;
+  cfg.pass_flops_budget = e.opt.pass_flops;
+  cfg.direct_io = true;
+  cfg.reg_bits = (e.opt.tile_kernel >= 2) ? 3 : 4;
+  return plan_passes(gates, cfg);
+}
+
+// Launches planned passes [first, last); `swap` (may be null) rides on the stores of the last one.
+static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t first, size_t last,
+                         const SwapStore *swap) {
+  if (first >= last) return QCS_CUDA_OK;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  const bool timed = e.timing && !e.opt.dryrun;
+  if (timed) {
+    ev0 = get_event(e);
+    ev1 = get_event(e);
+    cudaEventRecord(ev0, e.stream);
+  }
+  for (size_t k = first; k < last; k++) {
+    const PassPlan &p = plan[k];
+    if (!e.opt.dryrun) {
+      if (swap && k + 1 == last) {
+        if (timed) {  // the plain passes so far; the one that carries the swap is timed on its own
+          cudaEventRecord(ev1, e.stream);
+          e.pending_pass_events.emplace_back(ev0, ev1);
+          ev0 = get_event(e);
+          ev1 = get_event(e);
+          cudaEventRecord(ev0, e.stream);
+        }
+        SwapStore sw = *swap;
+        sw.lpos_in_tile = 0;
+        for (int pos : p.tile_positions)
+          if ((uint32_t)pos == sw.lpos) sw.lpos_in_tile = 1;
+        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, &sw));
+        RC(dist_after_fused_swap(e));
+      } else {
         CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel));
       }
-      e.passes++;
-      e.kernel_launches++;
-      e.segments += p.params.n_segments;
-      e.gates_executed += p.params.n_gates - p.n_fan_headers;
-      const double bytes = 32.0 * (double)e.local_size;
-      e.algorithmic_bytes += bytes;
-      e.pass_bytes += bytes;
     }
-    if (ev0) {
-      cudaEventRecord(ev1, e.stream);
-      e.pending_pass_events.emplace_back(ev0, ev1);
-      if (e.pending_pass_events.size() > 512) fold_events(e);
-    }
-    if (record_plan) {
-      for (auto &p : plan) e.last_plan.push_back(p);
-    }
+    e.passes++;
+    e.kernel_launches++;
+    e.segments += p.params.n_segments;
+    e.gates_executed += p.params.n_gates - p.n_fan_headers;
+    const double bytes = 32.0 * (double)e.local_size;
+    e.algorithmic_bytes += bytes;
+    e.pass_bytes += bytes;
+    e.last_plan.push_back(p);
+  }
+  if (ev0) {
+    cudaEventRecord(ev1, e.stream);
+    (swap ? e.pending_fused_events : e.pending_pass_events).emplace_back(ev0, ev1);
+    if (e.pending_pass_events.size() > 512) fold_events(e);
+  }
+  return QCS_CUDA_OK;
+}
+
+// Runs a list of physical gates whose pairing targets are all local.
+static int run_local(Engine &e, const std::vector<PhysGate> &gates) {
+  if (gates.empty()) return QCS_CUDA_OK;
+  if (e.opt.dryrun) trace_gates(e, gates);
+  const bool fused = e.opt.fusion && e.nl >= QCS_TILE_BITS;
+  if (fused) {
+    std::vector<PassPlan> plan = plan_batch(e, gates);
+    RC(launch_passes(e, plan, 0, plan.size(), nullptr));
   } else {
     for (const PhysGate &g : gates) {
       if (g.c.kind == GK_NOP) continue;
@@ -314,9 +356,8 @@ static int pick_victim(const Engine &e, const std::vector<HostGate> &q, size_t f
   return best;
 }
 
-static int swap_positions(Engine &e, int lpos, int gpos) {
-  if (!e.opt.dryrun) RC(dist_swap_positions(e, lpos, gpos));
-  else {
+static void note_swap(Engine &e, int lpos, int gpos) {
+  if (e.opt.dryrun) {
     Engine::TraceEntry t{};
     t.v[0] = 2.0;
     t.v[1] = (double)lpos;
@@ -330,25 +371,81 @@ static int swap_positions(Engine &e, int lpos, int gpos) {
   e.inv_perm[gpos] = ql;
   e.remaps++;
   e.exchange_bytes += 8.0 * (double)e.local_size;
+}
+
+static int swap_positions(Engine &e, int lpos, int gpos) {
+  if (!e.opt.dryrun) RC(dist_swap_positions(e, lpos, gpos));
+  note_swap(e, lpos, gpos);
   return QCS_CUDA_OK;
 }
 
-// Executes queue[begin, end): cuts at pairing gates whose target is global,
-// remaps, continues.
+// A swap can ride on the stores of a fused pass (SwapStore) when passes run through the plain-load
+// tile kernels and the partner's memory is mapped; plan-only engines follow the same schedule.
+static bool can_fuse_swaps(const Engine &e) {
+  if (!e.opt.fusion || e.nl < QCS_TILE_BITS || e.opt.sem != SEM_CORRECTED || e.opt.exchange != 1 ||
+      !e.opt.fuse_swaps)
+    return false;
+  if (e.opt.tile_kernel != 0 && e.opt.tile_kernel != 3) return false;
+  return e.opt.dryrun ? dist().active : (dist_p2p_available(e) && e.tile_flags != nullptr);
+}
+
+// Executes queue[begin, end).  A pairing gate whose target sits on a global position needs a
+// position swap first.  The swap does not get a kernel of its own when it can be avoided: it is
+// folded into the stores of a pass that runs anyway -- the EARLIEST pass after the victim
+// position's last pairing use, so that the NVLink transfer hides behind as much arithmetic as
+// possible and later swaps find later passes free.
 static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, size_t end) {
-  std::vector<PhysGate> batch;
-  for (size_t i = begin; i < end; i++) {
-    PhysGate p = to_phys(e, q[i]);
-    if (is_pairing_kind(p.c.kind) && p.tpos >= e.nl) {
-      RC(run_local(e, batch, true));
-      batch.clear();
-      const int victim = pick_victim(e, q, i);
-      RC(swap_positions(e, victim, p.tpos));
-      p = to_phys(e, q[i]);
+  const bool fuse = can_fuse_swaps(e);
+  size_t i = begin;
+  while (i < end) {
+    size_t x = i;  // first pairing gate on a global position under the current layout
+    std::vector<PhysGate> batch;
+    for (; x < end; x++) {
+      PhysGate p = to_phys(e, q[x]);
+      if (is_pairing_kind(p.c.kind) && p.tpos >= e.nl) break;
+      batch.push_back(p);
     }
-    batch.push_back(p);
+    if (x == end) return run_local(e, batch);
+    const int gpos = e.perm[q[x].target];
+    const int victim = pick_victim(e, q, x);
+    if (!fuse) {
+      RC(run_local(e, batch));
+      RC(swap_positions(e, victim, gpos));
+      i = x;
+      continue;
+    }
+    // the swap may happen anywhere after the last pairing gate on the victim position
+    size_t legal_from = i;
+    for (size_t k = i; k < x; k++)
+      if (is_pairing_kind(batch[k - i].c.kind) && batch[k - i].tpos == victim) legal_from = k + 1;
+    std::vector<PassPlan> plan = plan_batch(e, batch);
+    size_t pass_end = i, chosen = plan.size();
+    for (size_t k = 0; k < plan.size(); k++) {
+      pass_end += (size_t)plan[k].n_gates_api;
+      if (pass_end >= legal_from) {
+        chosen = k;
+        break;
+      }
+    }
+    if (chosen == plan.size()) {  // nothing to ride on (empty batch or only value-preserving gates)
+      if (e.opt.dryrun) trace_gates(e, batch);
+      RC(swap_positions(e, victim, gpos));
+      i = x;
+      continue;
+    }
+    SwapStore sw{};
+    if (!e.opt.dryrun && !dist_fused_swap_args(e, victim, gpos, sw)) {
+      RC(run_local(e, batch));
+      RC(swap_positions(e, victim, gpos));
+      i = x;
+      continue;
+    }
+    if (e.opt.dryrun) trace_gates(e, std::vector<PhysGate>(batch.begin(), batch.begin() + (long)(pass_end - i)));
+    RC(launch_passes(e, plan, 0, chosen + 1, &sw));
+    note_swap(e, victim, gpos);
+    e.fused_swaps++;
+    i = pass_end;  // the rest of the batch is planned again under the new layout
   }
-  RC(run_local(e, batch, true));
   return QCS_CUDA_OK;
 }
 
@@ -621,6 +718,7 @@ void qcs_cuda_state_destroy(qcs_cuda_engine *e) {
   }
   for (auto &pr : e->pending_pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto &pr : e->pending_xchg_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (auto &pr : e->pending_fused_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);
   for (auto ev : e->markers) if (ev) cudaEventDestroy(ev);
   pool_free(e->live, e->local_size * sizeof(double2));
@@ -905,6 +1003,8 @@ int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out) {
   out->pass_ms = e->pass_ms;
   out->exchange_bytes = e->exchange_bytes;
   out->exchange_ms = e->exchange_ms;
+  out->fused_remaps = e->fused_swaps;
+  out->fused_remap_pass_ms = e->fused_swap_pass_ms;
   return QCS_CUDA_OK;
 }
 
@@ -913,6 +1013,8 @@ int qcs_cuda_reset_stats(qcs_cuda_engine *e) {
   fold_events(*e);
   e->gates_submitted = e->gates_executed = e->passes = e->kernel_launches = e->segments = e->remaps = 0;
   e->algorithmic_bytes = e->pass_bytes = e->pass_ms = e->exchange_bytes = e->exchange_ms = 0;
+  e->fused_swaps = 0;
+  e->fused_swap_pass_ms = 0;
   return QCS_CUDA_OK;
 }
 

@@ -19,6 +19,7 @@ struct Options {
   bool dryrun = false;
   double pass_flops = 1000.0;  // FP64 work per amplitude a pass may fuse; measured flat above ~200 (scripts/budget_sweep.py): a pass costs max(memory, FP64), splitting it never helps
   int exchange = 0;  // 0: NCCL send/recv, 1: peer-memory swap kernel
+  bool fuse_swaps = true;  // fold position swaps into the stores of a pass (peer-memory path only)
   int tile_kernel = 3;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8), 3: ldg8 (512 thr x 8 amps, plain loads; default)
 };
 
@@ -45,8 +46,9 @@ struct Engine {
   double2 *staging = nullptr;  // half-shard exchange buffer (multi-GPU, NCCL path)
   std::vector<double2 *> peer_live;  // every rank's state buffer mapped through CUDA IPC (P2P path)
   cudaStream_t stream = nullptr;
-  cudaStream_t xstream = nullptr;  // exchanges pipelined against passes (multi-GPU)
-  cudaEvent_t slice_done[8] = {}, slice_swapped[8] = {}, slice_start = nullptr;
+  uint32_t *tile_flags = nullptr;         // one word per tile: handshake of passes that swap on the way out
+  std::vector<uint32_t *> peer_flags;     // every rank's tile_flags, peer-mapped
+  uint32_t swap_epoch = 0;
   ReduceWorkspace ws{};
   void *ws_slab = nullptr;       // one allocation backing every array of ws
   size_t ws_slab_bytes = 0;
@@ -66,7 +68,10 @@ struct Engine {
   // statistics
   long long gates_submitted = 0, gates_executed = 0, passes = 0, kernel_launches = 0,
             segments = 0, remaps = 0;
+  long long fused_swaps = 0;   // remaps that rode on a pass instead of getting a kernel of their own
   double algorithmic_bytes = 0, pass_bytes = 0, pass_ms = 0, exchange_bytes = 0, exchange_ms = 0;
+  double fused_swap_pass_ms = 0;  // device time of the passes that carried a swap (also in pass_ms)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_fused_events;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_pass_events;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_xchg_events;
@@ -88,7 +93,9 @@ int dist_allgather_host(const void *mine, void *all, size_t bytes_each);
 int dist_barrier(Engine &e);
 int dist_open_peers(Engine &e);
 bool dist_p2p_available(const Engine &e);
-int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos, uint64_t slice);
+int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos);
+bool dist_fused_swap_args(Engine &e, int lpos, int gpos, SwapStore &sw);
+int dist_after_fused_swap(Engine &e);
 void dist_close_peers(Engine &e);
 
 }  // namespace qcs

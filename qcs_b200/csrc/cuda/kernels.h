@@ -10,10 +10,20 @@ namespace qcs {
 // kernels_fused.cu ----------------------------------------------------------
 // variant 0: one CTA per tile, plain 128-bit global loads/stores
 // variant 1: persistent CTAs, tiles staged through shared memory by TMA bulk copies
-// slice: 0 = the whole shard; else a slice descriptor (kernels_fused.cu slice_expand) in tile-number
-// space -- only those tiles are processed (ldg variants), for pipelining passes with exchanges.
+// swap (ldg variants only, multi-GPU): the pass also performs a position swap with the partner rank
+// on its way out -- see SwapStore.
+struct SwapStore {
+  double2 *peer;              // partner's state buffer (peer-mapped); nullptr = plain pass
+  const uint32_t *my_flags;   // one word per tile: the partner's CTA writes `epoch` once it has loaded
+                              // the tile my results will overwrite
+  uint32_t *peer_flags;       // the partner's flag array (peer-mapped)
+  uint32_t epoch;             // value of this pass (strictly increasing per engine)
+  uint32_t lpos;              // local position traded for the partner-selecting rank bit
+  uint32_t my_gbit;           // my value of that rank bit
+  uint32_t lpos_in_tile;      // lpos is one of the pass's tile positions
+};
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
-                              cudaStream_t stream, int variant, uint64_t slice = 0);
+                              cudaStream_t stream, int variant, const SwapStore *swap = nullptr);
 
 // kernels_simple.cu: one launch per gate (fusion off, shards below one tile) ---
 cudaError_t launch_simple_gate(double2 *state, const DGate &g, int n_local,

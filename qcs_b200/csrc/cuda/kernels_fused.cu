@@ -53,20 +53,6 @@ __device__ __forceinline__ uint32_t swizzle(uint32_t slot) {
   return slot ^ (((slot >> 3) ^ (slot >> 6) ^ (slot >> 9)) & 7u);
 }
 
-// A slice of the shard = the tiles (or swap pairs) whose index has fixed values at up to three
-// bit positions.  Descriptor: pos0 | pos1 << 8 | pos2 << 16 | count << 24 | value << 32, positions
-// ascending.  Expands a dense index inside the slice to the full index.
-__host__ __device__ __forceinline__ uint64_t slice_expand(uint64_t dense, uint64_t desc) {
-  const uint32_t count = (uint32_t)(desc >> 24) & 0xffu;
-  const uint32_t value = (uint32_t)(desc >> 32);
-  for (uint32_t b = 0; b < count; b++) {
-    const uint32_t pos = (uint32_t)(desc >> (8 * b)) & 0xffu;
-    const uint64_t low = dense & ((1ull << pos) - 1ull);
-    dense = ((dense >> pos) << (pos + 1)) | low | ((uint64_t)((value >> b) & 1u) << pos);
-  }
-  return dense;
-}
-
 // Software bit-deposit: spreads the low bits of v over the set bits of mask.
 __device__ __forceinline__ uint64_t deposit_bits(uint64_t v, uint64_t mask) {
   uint64_t r = 0;
@@ -278,10 +264,11 @@ static int tile_row_bits(const PassParams &p) {
 }  // namespace
 
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
-                              cudaStream_t stream, int variant, uint64_t slice) {
-  const unsigned slice_bits = (unsigned)(slice >> 24) & 0xffu;
-  if (slice_bits && variant != 0 && variant != 3) return cudaErrorInvalidValue;  // ldg kernels only
-  const unsigned n_tiles = (1u << (n_local - QCS_TILE_BITS)) >> slice_bits;
+                              cudaStream_t stream, int variant, const SwapStore *swap) {
+  if (swap && variant != 0 && variant != 3) return cudaErrorInvalidValue;  // ldg kernels only
+  SwapStore sw{};
+  if (swap) sw = *swap;
+  const unsigned n_tiles = 1u << (n_local - QCS_TILE_BITS);
   static int sm_count = 0;
   static bool configured[4] = {false, false, false, false};
   if (variant < 0 || variant > 3) return cudaErrorInvalidValue;
@@ -315,7 +302,7 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
   }
   const unsigned grid = n_tiles < (unsigned)sm_count ? n_tiles : (unsigned)sm_count;
   if (variant == 0) {
-    fused_pass_ldg_r4<<<n_tiles, 256, smem_ldg, stream>>>(state, params, prefetch_distance(), stagger_ns(), (uint32_t)sm_count, slice);
+    fused_pass_ldg_r4<<<n_tiles, 256, smem_ldg, stream>>>(state, params, prefetch_distance(), stagger_ns(), (uint32_t)sm_count, sw);
   } else if (variant == 1) {
     fused_pass_tma_r4<<<grid, 256 + 32, smem_tma, stream>>>(state, params, n_tiles,
                                                             (uint32_t)tile_row_bits(params));
@@ -323,7 +310,7 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
     fused_pass_tma_r3<<<grid, 512 + 32, smem_tma, stream>>>(state, params, n_tiles,
                                                             (uint32_t)tile_row_bits(params));
   } else {
-    fused_pass_ldg_r3<<<n_tiles, 512, smem_ldg, stream>>>(state, params, prefetch_distance(), stagger_ns(), (uint32_t)sm_count, slice);
+    fused_pass_ldg_r3<<<n_tiles, 512, smem_ldg, stream>>>(state, params, prefetch_distance(), stagger_ns(), (uint32_t)sm_count, sw);
   }
   return cudaGetLastError();
 }

@@ -63,6 +63,26 @@ def main():
             if rank == 0:
                 print(f"done {name}/{fusion}/{exchange}: passes={st['passes']} remaps={st['remaps']}", flush=True)
             c.close(); orc.close()
+    # Larger shards (many tiles per rank): swaps ride on the stores of fused passes (SwapStore);
+    # the same circuits with stand-alone swap kernels must give the same bits.
+    big = {"random_19": (19, po.random_circuit_script(19, 10, seed=5)),
+           "qft_20": (20, [("x", 1), ("ry", 19, 0.3), ("h", 18), ("qft",)]),
+           "h_top_down_19": (19, [("h", q) for q in reversed(range(19))] + [("cnot", 3, 18), ("cnot", 18, 17)])}
+    for name, (n, script) in big.items():
+        orc = po.Oracle(n, "corrected")
+        po.replay(orc, script)
+        for fuse in ("on", "off"):
+            c = Circuit(n, semantics="corrected", fuse_swaps=fuse)
+            po.replay(c, script); c.flush(); st = c.stats()
+            first, count = c._shard()
+            got = c.state(); want = orc.state()[first:first + count]
+            check(np.all(got == want), f"{name}/fuse_swaps={fuse}: {int(np.sum(got != want))} shard amplitudes differ")
+            check((st["fused_remaps"] > 0) == (fuse == "on"), f"{name}/fuse_swaps={fuse}: fused_remaps={st['fused_remaps']}")
+            if rank == 0:
+                print(f"done {name}/fuse_swaps={fuse}: passes={st['passes']} remaps={st['remaps']} "
+                      f"fused={st['fused_remaps']}", flush=True)
+            c.close()
+        orc.close()
     # Grover across ranks (allreduced diffusion mean): tolerance 1e-12
     for sem in ("corrected", "reference"):
         n = 13
