@@ -390,6 +390,8 @@ def main() -> None:
         "passes_per_step": passes_per_step,
         "gates_per_pass": gates / passes_per_step if passes_per_step else None,
         "remaps_per_step": st["remaps"] / args.steps,
+        "fused_remaps_per_step": st["fused_remaps"] / args.steps,
+        "fused_remap_pass_ms": (st["fused_remap_pass_ms"] / st["fused_remaps"]) if st["fused_remaps"] else None,
         "roofline": {
             "bound": "hbm", "kernel": "fused_pass (tile kernel)",
             "achieved": pass_gbs, "peak": peak, "unit": "GB/s", "frac": pass_gbs / peak,
@@ -454,7 +456,13 @@ def random_circuit_aux(Circuit, kw, world, barrier, dist, torch) -> dict:
     return {"workload": f"{n}-qubit random circuit (H/RZ/CNOT brickwork, depth 40, {len(script)} gates)",
             "gates_per_s": len(script) / dev_s, "seconds": dev_s, "passes": st["passes"],
             "amplitude_gate_updates_per_s_per_gpu": len(script) * 2.0 ** n / dev_s / world,
-            "remaps": st["remaps"], "exchange_ms": st["exchange_ms"], "pass_ms": st["pass_ms"],
+            "remaps": st["remaps"], "fused_remaps": st["fused_remaps"],
+            "fused_remap_pass_ms_avg": (st["fused_remap_pass_ms"] / st["fused_remaps"]) if st["fused_remaps"] else None,
+            "nvlink_GBps_per_direction_in_fused_passes": (st["fused_remaps"] * 8.0 * 2.0 ** (n - int(math.log2(world)))
+                                                          / (st["fused_remap_pass_ms"] * 1e-3) / 1e9
+                                                          if st["fused_remap_pass_ms"] else None),
+            "plain_pass_ms_avg": ((st["pass_ms"] - st["fused_remap_pass_ms"]) / max(1, st["passes"] - st["fused_remaps"])),
+            "exchange_ms": st["exchange_ms"], "pass_ms": st["pass_ms"],
             "pass_GBps": st["pass_bytes"] / (st["pass_ms"] * 1e-3) / 1e9 if st["pass_ms"] else None,
             "exchange_GBps_per_direction": (st["exchange_bytes"] / (st["exchange_ms"] * 1e-3) / 1e9
                                             if st["exchange_ms"] else None)}

@@ -333,23 +333,26 @@ static int run_local(Engine &e, const std::vector<PhysGate> &gates) {
   return QCS_CUDA_OK;
 }
 
-// Picks the local position to trade for global position `gpos`: the local
-// qubit whose next use as a pairing target lies farthest ahead in the queue.
-static int pick_victim(const Engine &e, const std::vector<HostGate> &q, size_t from) {
-  std::vector<long> next_use(e.nl, (long)q.size() + 1);
-  for (size_t i = q.size(); i-- > from;) {
+// Picks the local position to trade for a global one at queue index `from`: the position whose
+// next use as a pairing target lies farthest ahead.  Among equally idle ones, the one whose last
+// pairing use since `since` lies farthest BACK (the swap may then ride on an earlier pass), then
+// the highest (long contiguous rows stay intact).  Never positions 0..4 (lane bits of every tile).
+static int pick_victim(const Engine &e, const std::vector<HostGate> &q, size_t from, size_t since) {
+  std::vector<long> next_use(e.nl, (long)q.size() + 1), last_use(e.nl, -1);
+  for (size_t i = q.size(); i-- > since;) {
     Classified c = classify_gate(q[i].m, q[i].control >= 0, e.opt.sem);
     if (!is_pairing_kind(c.kind)) continue;
     int pos = e.perm[q[i].target];
-    if (pos < e.nl) next_use[pos] = (long)i;
+    if (pos >= e.nl) continue;
+    if (i >= from) next_use[pos] = (long)i;
+    else if (last_use[pos] < 0) last_use[pos] = (long)i;
   }
   int best = e.nl - 1;
-  long best_use = -1;
-  // Prefer high positions (long contiguous rows stay intact) among equally idle ones;
-  // never trade positions 0..4 (lane bits of every tile).
+  long best_next = -1, best_last = 0;
   for (int pos = e.nl - 1; pos >= QCS_LANE_BITS && pos >= 0; pos--) {
-    if (next_use[pos] > best_use) {
-      best_use = next_use[pos];
+    if (next_use[pos] > best_next || (next_use[pos] == best_next && last_use[pos] < best_last)) {
+      best_next = next_use[pos];
+      best_last = last_use[pos];
       best = pos;
     }
   }
@@ -407,7 +410,7 @@ static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, si
     }
     if (x == end) return run_local(e, batch);
     const int gpos = e.perm[q[x].target];
-    const int victim = pick_victim(e, q, x);
+    const int victim = pick_victim(e, q, x, i);
     if (!fuse) {
       RC(run_local(e, batch));
       RC(swap_positions(e, victim, gpos));
