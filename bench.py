@@ -35,6 +35,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_JSON_OUT = sys.stdout
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -241,7 +242,7 @@ def reference_arm(args, rank: int, world: int) -> None:
         "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "modes": modes,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -262,6 +263,12 @@ def main() -> None:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: native libraries (NCCL's version banner) that write to
+    # file descriptor 1 are sent to stderr, the JSON goes out through a private copy of the descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         reference_arm(args, rank, world)
@@ -354,7 +361,7 @@ def main() -> None:
     e2e_value = gates * world * e2e_steps / e2e_s
     passes_per_step = st["passes"] / args.steps
     # host->device traffic of a step = the gate descriptors, shipped as kernel parameter blocks
-    h2d_per_step = int(passes_per_step * PASS_PARAM_BYTES)
+    h2d_per_step = int(passes_per_step * C.qcs_cuda_pass_descriptor_bytes())
 
     aux = None
     if (world > 1 or args.aux) and not args.skip_aux:
@@ -373,6 +380,17 @@ def main() -> None:
     else:
         peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
     n_local = n - int(math.log2(world))
+    # FP64 ceiling of the same kernel: the gate arithmetic is separately rounded mul / add (no FMA:
+    # bit-exactness), so the ceiling is the issue rate of such instructions, measured by a probe kernel
+    fp64_peak = ctypes.c_double(0.0)
+    fp64 = None
+    if C.qcs_cuda_probe_fp64(ctypes.byref(fp64_peak)) == 0 and st["pass_ms"] > 0:
+        ops = st["pass_flops_per_amp"] * 2.0 ** n_local
+        fp64 = {"achieved": ops / (st["pass_ms"] * 1e-3) / 1e12, "peak": fp64_peak.value / 1e12,
+                "unit": "Tops/s (separately rounded FP64 mul/add, FMA not allowed)",
+                "frac": ops / (st["pass_ms"] * 1e-3) / fp64_peak.value,
+                "ops_per_amplitude_per_step": st["pass_flops_per_amp"] / args.steps,
+                "peak_source": "measured in this run (qcs_cuda_probe_fp64: mul.rn/add.rn chains, no memory traffic)"}
     line = {
         "metric": "gates/s", "value": value, "unit": "gates/s", "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * dev_s / args.steps,
@@ -400,6 +418,7 @@ def main() -> None:
             "avg_launch_ms": st["pass_ms"] / st["passes"] if st["passes"] else None,
             "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(n_local),
             "share_of_step": (st["pass_ms"] * 1e-3) / dev_s if dev_s > 0 else None,
+            "co_limiter_fp64": fp64,
         },
         "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": h2d_per_step,
                 "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps,
@@ -418,17 +437,15 @@ def main() -> None:
         except Exception as exc:  # the baseline is a report, never a reason to lose the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "gates/s", "cores": 0, "kind": "reference",
                                     "sample": f"failed: {exc}"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         C.qcs_cuda_dist_finalize()
         dist.destroy_process_group()
 
 
-# sizeof(PassParams) in qcs_b200/csrc/cuda/common.h: header + 12 segments + 121 gate slots
-PASS_PARAM_BYTES = 48 + 48 + 2 * 3 * 8 * 8 + 2 * 4 * 8 + 12 * 80 + 145 * 72
 # dram__bytes_read.sum + dram__bytes_write.sum per fused-pass launch, from the ncu --set full
 # captures committed under profiles/ (keyed by local qubits); None where not captured.
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {28: 8.53e9}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {28: 8.53e9, 30: 34.30e9}  # profiles/r1g_qft30_ldg8_summary.csv
 
 
 def random_circuit_aux(Circuit, kw, world, barrier, dist, torch) -> dict:

@@ -126,6 +126,8 @@ typedef struct qcs_cuda_stats {
   long fused_remaps;           /* remaps folded into the stores of a pass    */
   double fused_remap_pass_ms;  /* device time of the passes that carried one
                                   (also counted in pass_ms)                  */
+  double pass_flops_per_amp;   /* separately rounded FP64 operations per
+                                  amplitude, summed over executed passes     */
 } qcs_cuda_stats;
 
 int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out);
@@ -139,6 +141,12 @@ int qcs_cuda_set_timing(qcs_cuda_engine *e, int enabled);
 int qcs_cuda_marker_record(qcs_cuda_engine *e, int slot);
 int qcs_cuda_marker_elapsed_ms(qcs_cuda_engine *e, int from_slot, int to_slot,
                                double *ms);
+
+/* Measures this GPU's issue rate of separately rounded FP64 operations (mul.rn / add.rn, never
+ * fused): the arithmetic ceiling of the gate kernels, reported by bench.py beside the HBM one. */
+int qcs_cuda_probe_fp64(double *ops_per_second);
+/* sizeof the kernel-parameter block that describes one fused pass (what a flush ships to the GPU). */
+long qcs_cuda_pass_descriptor_bytes(void);
 
 /* Writes a human-readable description of the passes the last flush executed
  * (tile bits, segments, gates per segment) into buf; returns bytes needed. */
@@ -174,6 +182,10 @@ int qcs_cuda_dist_world(void);
  * points above next to the qcs.h API (tests, bench.py). */
 struct t_q_circuit;
 qcs_cuda_engine *qc_cuda_engine(struct t_q_circuit *circuit);
+/* qc_run_shots without the dense 2^n histogram (reference src/qcs.c:575-607 draws and decides the
+ * same way): indices[s] = outcome of shot s, or -1 where the reference drops the shot.  Consumes
+ * `shots` values of rand(), like qc_run_shots. */
+void qc_run_shots_sparse(struct t_q_circuit *circuit, int shots, long *indices);
 
 #ifdef __cplusplus
 }

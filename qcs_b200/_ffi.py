@@ -30,6 +30,7 @@ class Stats(ctypes.Structure):
         ("algorithmic_bytes", _D), ("pass_bytes", _D), ("pass_ms", _D),
         ("exchange_bytes", _D), ("exchange_ms", _D),
         ("fused_remaps", ctypes.c_long), ("fused_remap_pass_ms", _D),
+        ("pass_flops_per_amp", _D),
     ]
 
     def as_dict(self) -> dict:
@@ -62,6 +63,8 @@ CUDA_ABI = {
     "qcs_cuda_set_timing": (_I, [_P, _I]),
     "qcs_cuda_marker_record": (_I, [_P, _I]),
     "qcs_cuda_marker_elapsed_ms": (_I, [_P, _I, _I, _DP]),
+    "qcs_cuda_probe_fp64": (_I, [_DP]),
+    "qcs_cuda_pass_descriptor_bytes": (_L, []),
     "qcs_cuda_describe_last_plan": (_L, [_P, ctypes.c_char_p, _L]),
     "qcs_cuda_last_error": (ctypes.c_char_p, []),
     "qcs_cuda_dist_unique_id": (_I, [ctypes.c_char_p]),
@@ -93,6 +96,7 @@ HOST_API = {
     "qc_cphase": (None, [_P, _I, _I, _D]),
     "qc_add_gate": (None, [_P, ctypes.c_char_p, _I, _I, _D]),
     "qc_cuda_engine": (_P, [_P]),
+    "qc_run_shots_sparse": (None, [_P, _I, _LP]),
 }
 
 _cuda = None

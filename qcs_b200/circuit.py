@@ -100,6 +100,12 @@ class Circuit:
         self.H.qc_run_shots(self.c, shots, res.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
         return res
 
+    def run_shots_sparse(self, shots: int) -> np.ndarray:
+        """Outcome of every shot (-1: dropped by the reference's rule), no dense histogram."""
+        idx = np.empty(shots, dtype=np.int64)
+        self.H.qc_run_shots_sparse(self.c, shots, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_long)))
+        return idx
+
     # -- state access -----------------------------------------------------------------
     def find_most_likely_state(self) -> int: return self.H.qc_find_most_likely_state(self.c)
     def get_probability(self, state: int) -> float: return self.H.qc_get_probability(self.c, state)

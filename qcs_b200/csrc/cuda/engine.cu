@@ -294,6 +294,7 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
     const double bytes = 32.0 * (double)e.local_size;
     e.algorithmic_bytes += bytes;
     e.pass_bytes += bytes;
+    e.pass_flops_per_amp += p.flops_per_amp;
     e.last_plan.push_back(p);
   }
   if (ev0) {
@@ -1008,6 +1009,7 @@ int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out) {
   out->exchange_ms = e->exchange_ms;
   out->fused_remaps = e->fused_swaps;
   out->fused_remap_pass_ms = e->fused_swap_pass_ms;
+  out->pass_flops_per_amp = e->pass_flops_per_amp;
   return QCS_CUDA_OK;
 }
 
@@ -1018,6 +1020,7 @@ int qcs_cuda_reset_stats(qcs_cuda_engine *e) {
   e->algorithmic_bytes = e->pass_bytes = e->pass_ms = e->exchange_bytes = e->exchange_ms = 0;
   e->fused_swaps = 0;
   e->fused_swap_pass_ms = 0;
+  e->pass_flops_per_amp = 0;
   return QCS_CUDA_OK;
 }
 
@@ -1039,6 +1042,38 @@ int qcs_cuda_marker_elapsed_ms(qcs_cuda_engine *e, int from_slot, int to_slot, d
   *ms = (double)f;
   return QCS_CUDA_OK;
 }
+
+int qcs_cuda_probe_fp64(double *ops_per_second) {
+  if (!ops_per_second) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
+  int dev = 0, sms = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, iters = 1 << 14;
+  double *out = nullptr;
+  CK(cudaMalloc(&out, (size_t)blocks * 256 * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  cudaError_t err = cudaSuccess;
+  for (int rep = 0; rep < 4 && err == cudaSuccess; rep++) {  // first repetition warms up
+    cudaEventRecord(e0, 0);
+    err = launch_fp64_probe(out, blocks, iters, 0);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  CK(err);
+  *ops_per_second = 16.0 * iters * 256.0 * blocks / (best * 1e-3);
+  return QCS_CUDA_OK;
+}
+
+long qcs_cuda_pass_descriptor_bytes(void) { return (long)sizeof(PassParams); }
 
 long qcs_cuda_trace_read(qcs_cuda_engine *e, long index, double out[12]) {
   if (!e) return 0;

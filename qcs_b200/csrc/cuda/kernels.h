@@ -30,6 +30,8 @@ cudaError_t launch_simple_gate(double2 *state, const DGate &g, int n_local,
                                uint64_t shard_base, cudaStream_t stream);
 
 cudaError_t launch_swap_local_bits(double2 *state, int n_local, int a, int b, cudaStream_t stream);
+// `out` must hold blocks * 256 doubles; every thread performs 16 * iters separately rounded FP64 ops
+cudaError_t launch_fp64_probe(double *out, int blocks, int iters, cudaStream_t stream);
 
 // kernels_reduce.cu -----------------------------------------------------------
 struct ReduceWorkspace {

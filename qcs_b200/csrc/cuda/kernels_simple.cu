@@ -78,7 +78,30 @@ swap_local_bits_kernel(double2 *__restrict__ state, int a, int b, uint64_t n_ite
   }
 }
 
+// Issue-rate probe: 8 independent dependency chains of mul.rn.f64 / add.rn.f64 per thread, no
+// memory traffic.  bench.py reports the measured rate as the FP64 ceiling of the fused pass, whose
+// arithmetic may not be contracted into FMAs (bit-exactness) and therefore cannot use the
+// datasheet's FMA-counted FP64 figure.
+__global__ void __launch_bounds__(256)
+fp64_probe_kernel(double *__restrict__ out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+  for (int i = 0; i < iters; i++) {
+    x0 = __dadd_rn(__dmul_rn(x0, a), b); x1 = __dadd_rn(__dmul_rn(x1, a), b);
+    x2 = __dadd_rn(__dmul_rn(x2, a), b); x3 = __dadd_rn(__dmul_rn(x3, a), b);
+    x4 = __dadd_rn(__dmul_rn(x4, a), b); x5 = __dadd_rn(__dmul_rn(x5, a), b);
+    x6 = __dadd_rn(__dmul_rn(x6, a), b); x7 = __dadd_rn(__dmul_rn(x7, a), b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 }  // namespace
+
+cudaError_t launch_fp64_probe(double *out, int blocks, int iters, cudaStream_t stream) {
+  fp64_probe_kernel<<<blocks, 256, 0, stream>>>(out, iters, 0.9999999, 1e-9);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_swap_local_bits(double2 *state, int n_local, int a, int b, cudaStream_t stream) {
   if (a == b) return cudaSuccess;

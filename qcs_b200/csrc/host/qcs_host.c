@@ -292,6 +292,24 @@ void qc_run_shots(t_q_circuit *circuit, int shots, int *results) {
   free(idx);
 }
 
+/* Sparse companion of qc_run_shots: the same draws, the same
+ * decisions, but the outcome of shot s is written to indices[s] (-1: the reference drops that
+ * shot) instead of a dense 2^n histogram -- at 32 qubits the histogram alone is 16 GiB that
+ * the callee must zero.  Not part of include/qcs.h; declared in include/qcs_cuda.h. */
+void qc_run_shots_sparse(t_q_circuit *circuit, int shots, long *indices) {
+  double *u;
+  int s;
+  if (!circuit || shots <= 0 || !indices)
+    return;
+  u = (double *)malloc((size_t)shots * sizeof(double));
+  if (!u)
+    return;
+  for (s = 0; s < shots; s++)
+    u[s] = rand() / (double)RAND_MAX;
+  report("qc_run_shots_sparse", qcs_cuda_sample(circuit->engine, u, shots, indices));
+  free(u);
+}
+
 /* ---- state access (reference src/qcs.c:391-395, 464-478) -------------------- */
 
 double qc_get_probability(t_q_circuit *circuit, int state) {

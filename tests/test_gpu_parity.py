@@ -205,6 +205,25 @@ def test_dropped_shots_like_reference():
     c.close()
 
 
+def test_sparse_shots_match_the_dense_histogram():
+    """qc_run_shots_sparse: per-shot outcomes whose histogram is qc_run_shots', dropped
+    shots marked -1; same rand() consumption (the next measurement draws the same number)."""
+    n = 14
+    script = po.random_circuit_script(n, 3, seed=8)
+    for sem in ("reference", "corrected"):
+        c = Circuit(n, semantics=sem); po.replay(c, script)
+        po.srand(31); dense = c.run_shots(5000); m_dense = c.measure(3)
+        c.close()
+        c = Circuit(n, semantics=sem); po.replay(c, script)
+        po.srand(31); idx = c.run_shots_sparse(5000); m_sparse = c.measure(3)
+        c.close()
+        assert idx.shape == (5000,) and idx.min() >= -1 and idx.max() < (1 << n)
+        hist = np.bincount(idx[idx >= 0], minlength=1 << n)
+        assert np.array_equal(hist, dense)
+        assert int(np.sum(idx < 0)) == 5000 - int(dense.sum())
+        assert m_dense == m_sparse
+
+
 def test_fusion_on_off_identical_large():
     """26 qubits (1 GiB): fused passes vs one kernel per gate, every amplitude equal."""
     n = 26
