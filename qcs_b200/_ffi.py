@@ -30,7 +30,7 @@ class Stats(ctypes.Structure):
         ("algorithmic_bytes", _D), ("pass_bytes", _D), ("pass_ms", _D),
         ("exchange_bytes", _D), ("exchange_ms", _D),
         ("fused_remaps", ctypes.c_long), ("fused_remap_pass_ms", _D),
-        ("pass_flops_per_amp", _D),
+        ("pass_flops_per_amp", _D), ("gates_cancelled", ctypes.c_long),
     ]
 
     def as_dict(self) -> dict:

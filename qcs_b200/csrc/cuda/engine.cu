@@ -86,6 +86,8 @@ static int load_options(Options &o) {
   else return set_error(QCS_CUDA_ERR_INVALID, "exchange must be p2p|nccl, got '%s'", v.c_str());
   v = option_value("fuse_swaps");
   o.fuse_swaps = !(v == "off" || v == "0");
+  v = option_value("peephole");
+  o.peephole = !(v == "off" || v == "0");
   return QCS_CUDA_OK;
 }
 
@@ -453,11 +455,64 @@ static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, si
   return QCS_CUDA_OK;
 }
 
+// Queue-level peephole: drops pairs of identical gates that undo each
+// other EXACTLY, before they cost a pass.  Only gates that permute or negate amplitudes qualify
+// (X, Y, Z, and their controlled forms: exact X is a move, exact -1 / +-i factors round nothing),
+// so the surviving gates see bit-identical inputs; H.H is NOT dropped -- it is the identity only
+// up to rounding, and the reference computes it.  Two such gates cancel when every gate between
+// them leaves their qubits alone (a permutation / sign flip of qubit a commutes exactly with
+// arithmetic that does not involve a).  Corrected semantics only: under `reference` semantics a
+// controlled-X is not an involution and the scratch buffer makes the last gate observable.
+// The reference's own qc_optimize edits only its history (src/qcs.c:650-698); the host layer keeps
+// that behaviour, this pass never changes qc_get_num_gates.
+static bool exact_involution(const HostGate &g) {
+  const double *m = g.m;
+  auto is = [&](int k, double re, double im) { return m[2 * k] == re && m[2 * k + 1] == im; };
+  if (is(0, 0, 0) && is(3, 0, 0)) {
+    if (is(1, 1, 0) && is(2, 1, 0)) return true;    // X
+    if (is(1, 0, -1) && is(2, 0, 1)) return true;   // Y
+  }
+  if (is(1, 0, 0) && is(2, 0, 0) && is(0, 1, 0) && is(3, -1, 0)) return true;  // Z
+  return false;
+}
+
+static size_t cancel_exact_pairs(std::vector<HostGate> &q) {
+  const size_t before = q.size();
+  std::vector<char> dead(q.size(), 0);
+  auto touches = [](const HostGate &g, int qubit) { return g.target == qubit || g.control == qubit; };
+  for (bool changed = true; changed;) {
+    changed = false;
+    for (size_t i = 0; i < q.size(); i++) {
+      if (dead[i] || !exact_involution(q[i])) continue;
+      for (size_t j = i + 1; j < q.size(); j++) {
+        if (dead[j]) continue;
+        const bool involved = touches(q[j], q[i].target) || (q[i].control >= 0 && touches(q[j], q[i].control));
+        if (!involved) continue;
+        if (q[j].target == q[i].target && q[j].control == q[i].control &&
+            std::memcmp(q[j].m, q[i].m, sizeof(q[i].m)) == 0) {
+          dead[i] = dead[j] = 1;
+          changed = true;
+        }
+        break;  // the first gate that involves these qubits decides
+      }
+    }
+  }
+  size_t w = 0;
+  for (size_t i = 0; i < q.size(); i++)
+    if (!dead[i]) q[w++] = q[i];
+  q.resize(w);
+  return before - w;
+}
+
 static int flush(Engine &e) {
   if (e.queue.empty()) return QCS_CUDA_OK;
   std::vector<HostGate> q;
   q.swap(e.queue);
   e.last_plan.clear();
+  if (e.opt.sem == SEM_CORRECTED && e.opt.peephole) {
+    e.gates_cancelled += (long long)cancel_exact_pairs(q);
+    if (q.empty()) return QCS_CUDA_OK;
+  }
   if (e.opt.sem == SEM_REFERENCE) {
     // Scratch-observability rule: after any gate the
     // reference's scratch buffer holds the complete pre-gate state.  Execute
@@ -1010,6 +1065,7 @@ int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out) {
   out->fused_remaps = e->fused_swaps;
   out->fused_remap_pass_ms = e->fused_swap_pass_ms;
   out->pass_flops_per_amp = e->pass_flops_per_amp;
+  out->gates_cancelled = e->gates_cancelled;
   return QCS_CUDA_OK;
 }
 
@@ -1019,6 +1075,7 @@ int qcs_cuda_reset_stats(qcs_cuda_engine *e) {
   e->gates_submitted = e->gates_executed = e->passes = e->kernel_launches = e->segments = e->remaps = 0;
   e->algorithmic_bytes = e->pass_bytes = e->pass_ms = e->exchange_bytes = e->exchange_ms = 0;
   e->fused_swaps = 0;
+  e->gates_cancelled = 0;
   e->fused_swap_pass_ms = 0;
   e->pass_flops_per_amp = 0;
   return QCS_CUDA_OK;

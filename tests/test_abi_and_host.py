@@ -134,3 +134,31 @@ def test_invalid_gates_are_recorded_but_not_queued(libs):
     assert c.num_gates == 4
     c.flush()
     assert c.stats()["gates_submitted"] == 1
+
+
+def test_single_header_bundle_compiles_as_c89(tmp_path):
+    """scripts/bundle.py emits one qcs.h; a C89 program that defines
+    QCS_IMPLEMENTATION builds against it and links only libqcs_cuda.so.  Without a GPU qc_create
+    must fail loudly (NULL + message), never fall back to the CPU."""
+    import subprocess, sys, shutil
+    from qcs_b200 import build
+    build.build_all()
+    hdr = tmp_path / "qcs.h"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "scripts", "bundle.py"), str(hdr)])
+    prog = tmp_path / "prog.c"
+    prog.write_text('#define QCS_IMPLEMENTATION\n#include "qcs.h"\n#include <stdio.h>\n'
+                    'int main(void) { t_q_circuit *c = qc_create(3);\n'
+                    '  if (!c) { printf("no device\\n"); return 0; }\n'
+                    '  qc_h(c, 0); qc_cnot(c, 0, 1); printf("%d %d\\n", qc_get_num_gates(c), qc_find_most_likely_state(c));\n'
+                    '  qc_destroy(c); return 0; }\n')
+    exe = tmp_path / "prog"
+    lib = os.path.join(ROOT, "qcs_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c89", "-pedantic", "-Wall", "-ffp-contract=off", "-I", str(tmp_path),
+                           str(prog), "-L" + lib, "-lqcs_cuda", "-lm", "-Wl,-rpath," + lib, "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        assert "no device" in r.stdout and "Error" in r.stderr
+    else:
+        assert r.stdout.split()[0] == "2"

@@ -205,6 +205,25 @@ def test_dropped_shots_like_reference():
     c.close()
 
 
+def test_queue_peephole_is_value_preserving():
+    """Cancelling exact X/Y/Z/CNOT pairs in the queue must not change one bit."""
+    n = 15
+    rng = np.random.default_rng(17)
+    script = []
+    for op in po.random_circuit_script(n, 5, seed=23):
+        script.append(op)
+        r = rng.integers(0, 6)
+        q = int(rng.integers(0, n)); p = int((q + 1 + rng.integers(0, n - 1)) % n)
+        pair = [("x", q), ("y", q), ("z", q), ("cnot", q, p)][r] if r < 4 else None
+        if pair:                                   # pair split by a gate on another qubit
+            script += [pair, ("rz", (q + 2) % n if (q + 2) % n != p else (q + 3) % n, 0.37), pair]
+    orc = po.Oracle(n, "corrected"); po.replay(orc, script)
+    c = Circuit(n, semantics="corrected"); po.replay(c, script); c.flush()
+    assert c.stats()["gates_cancelled"] > 0
+    assert _same(c.state(), orc.state())
+    c.close(); orc.close()
+
+
 def test_sparse_shots_match_the_dense_histogram():
     """qc_run_shots_sparse: per-shot outcomes whose histogram is qc_run_shots', dropped
     shots marked -1; same rand() consumption (the next measurement draws the same number)."""

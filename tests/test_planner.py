@@ -106,3 +106,22 @@ def test_pass_flops_budget_splits_passes():
     few = _parse(_plan(14, script, semantics="corrected", pass_flops=1000)[0])
     many = _parse(_plan(14, script, semantics="corrected", pass_flops=40)[0])
     assert len(many) > len(few)
+
+
+def test_queue_peephole_drops_only_exact_pairs():
+    """X.X / Y.Y / Z.Z / CNOT.CNOT vanish from the queue (corrected semantics) when
+    nothing between them involves their qubits; H.H (identity only up to rounding) stays."""
+    def executed(script, **kw):
+        _, st = _plan(14, script, semantics="corrected", **kw)
+        return st["gates_executed"], st["gates_cancelled"]
+    assert executed([("x", 3), ("h", 5), ("x", 3)]) == (1, 2)
+    assert executed([("y", 2), ("z", 4), ("rz", 7, 0.3), ("z", 4), ("y", 2)]) == (1, 4)
+    assert executed([("cnot", 1, 6), ("h", 9), ("cnot", 1, 6)]) == (1, 2)
+    assert executed([("x", 3), ("cnot", 3, 4), ("x", 3)]) == (3, 0)      # the CNOT reads qubit 3
+    assert executed([("cnot", 1, 6), ("rz", 6, 0.1), ("cnot", 1, 6)]) == (3, 0)
+    assert executed([("h", 3), ("h", 3)]) == (2, 0)
+    assert executed([("x", 3), ("x", 3), ("x", 3)]) == (1, 2)
+    assert executed([("x", 3), ("h", 5), ("x", 3)], peephole="off") == (3, 0)
+    # reference semantics: never (a controlled X is not an involution there, the scratch buffer is observable)
+    _, st = _plan(14, [("x", 3), ("x", 3)], semantics="reference")
+    assert st["gates_executed"] == 2 and st["gates_cancelled"] == 0
