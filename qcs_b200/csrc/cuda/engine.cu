@@ -86,6 +86,9 @@ static int load_options(Options &o) {
   else return set_error(QCS_CUDA_ERR_INVALID, "exchange must be p2p|nccl, got '%s'", v.c_str());
   v = option_value("fuse_swaps");
   o.fuse_swaps = !(v == "off" || v == "0");
+  v = option_value("fixed_low");
+  if (!v.empty()) o.fixed_low = std::atoi(v.c_str());
+  if (o.fixed_low < 1 || o.fixed_low > QCS_LANE_BITS) o.fixed_low = Options().fixed_low;
   v = option_value("peephole");
   o.peephole = !(v == "off" || v == "0");
   return QCS_CUDA_OK;
@@ -254,6 +257,7 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
   cfg.pass_flops_budget = e.opt.pass_flops;
   cfg.direct_io = true;
   cfg.reg_bits = (e.opt.tile_kernel >= 2) ? 3 : 4;
+  cfg.fixed_low = e.opt.fixed_low;
   return plan_passes(gates, cfg);
 }
 

@@ -19,6 +19,7 @@ struct Options {
   bool dryrun = false;
   double pass_flops = 1000.0;  // FP64 work per amplitude a pass may fuse; measured flat above ~200 (scripts/budget_sweep.py): a pass costs max(memory, FP64), splitting it never helps
   int exchange = 0;  // 0: NCCL send/recv, 1: peer-memory swap kernel
+  int fixed_low = 5;       // positions every tile contains (contiguous global rows of 16 << fixed_low bytes)
   bool peephole = true;    // drop exactly self-cancelling gate pairs from the queue (corrected semantics)
   bool fuse_swaps = true;  // fold position swaps into the stores of a pass (peer-memory path only)
   int tile_kernel = 3;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8), 3: ldg8 (512 thr x 8 amps, plain loads; default)

@@ -157,10 +157,19 @@ struct PassBuilder {
   double flops = 0.0;
 
   explicit PassBuilder(const PlannerConfig &c) : cfg(c) {
-    for (int p = 0; p < QCS_LANE_BITS; p++) tile.push_back(p);
+    for (int p = 0; p < cfg.fixed_low; p++) tile.push_back(p);
   }
   bool has(int pos) const { return std::find(tile.begin(), tile.end(), pos) != tile.end(); }
   bool empty() const { return gates.empty() && n_api == 0; }
+
+  // one of the five lowest positions of the tile as it stands (a conservative stand-in for "lane
+  // bit of the I/O segments": a lower position may still join the tile later)
+  bool low5(int pos) const {
+    int below = 0;
+    for (int p : tile)
+      if (p < pos) below++;
+    return below < QCS_LANE_BITS;
+  }
 
   // Counts the segments the current gate list needs (plus the I/O segments).
   int segments_needed(const PhysGate *extra) const {
@@ -177,7 +186,7 @@ struct PassBuilder {
         last_low = false;
       }
       r[in_r++] = g.tpos;
-      if (g.tpos < QCS_LANE_BITS) {
+      if (low5(g.tpos)) {
         if (segs == 1) first_low = true;
         last_low = true;
       }
@@ -208,7 +217,7 @@ struct PassBuilder {
     PassPlan plan;
     std::memset(&plan.params, 0, sizeof(plan.params));
     // Fill the tile with the lowest unused local positions (keeps rows long).
-    for (int p = QCS_LANE_BITS; (int)tile.size() < QCS_TILE_BITS && p < cfg.n_local; p++)
+    for (int p = cfg.fixed_low; (int)tile.size() < QCS_TILE_BITS && p < cfg.n_local; p++)
       if (!has(p)) tile.push_back(p);
     std::sort(tile.begin(), tile.end());
     plan.tile_positions = tile;

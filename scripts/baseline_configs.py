@@ -1,0 +1,114 @@
+"""BASELINE.json configs 1-3 on one GPU, the reference's CPU modes timed beside them on this
+box's host cores (oracle/_ref: the unmodified reference built by oracle/Makefile; absent -> GPU only).
+
+  python scripts/baseline_configs.py [--skip-cpu] > gpurun_out/baseline_configs.json
+
+Config 1: 20 qubits, the README's "Deutsch-Jozsa" benchmark as SURVEY 8(d) defines it through the
+          public API: qc_bernstein_vazirani(0x55555) + qc_run (20 collapsing measurements), timed
+          create -> run end to end; measured bits compared with the reference run on the same seed.
+Config 2: 24-qubit qc_grover_search(0xABCDE): 24 H + 3216 x (phase flip + diffusion).
+Config 3: 30-qubit qc_quantum_fourier_transform (bench.py is the contract line for this one).
+Semantics: `reference` for configs 1-2 where parity with the unmodified reference is checked,
+`corrected` where throughput is quoted."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from qcs_b200 import Circuit
+from oracle import pyoracle as po
+
+skip_cpu = "--skip-cpu" in sys.argv
+cores = os.cpu_count() or 1
+out = {"host_cores": cores}
+
+
+def timed(f):
+    t0 = time.perf_counter(); r = f(); return r, time.perf_counter() - t0
+
+
+# ---------------------------------------------------------------- config 1
+def dj_gpu(sem):
+    po.srand(20)
+    c = Circuit(20, semantics=sem)
+    c.bv(0x55555 & 0x7FFFF)
+    bits = c.measure_all()
+    n_gates = c.num_gates
+    c.close()
+    return bits, n_gates
+
+dj_gpu("reference")                                   # warm-up (library load, context)
+cfg1 = {}
+for sem in ("reference", "corrected"):
+    (bits, n_gates), dt = timed(lambda: dj_gpu(sem))
+    cfg1[f"gpu_{sem}_s"] = dt
+    cfg1[f"gpu_{sem}_bits"] = "".join(map(str, bits))
+    cfg1["history_entries"] = n_gates
+if not skip_cpu:
+    for mode in ("seq", "simd", "omp", "mt", "corrected"):
+        if not po.ref_available(mode):
+            continue
+        if mode == "omp":
+            os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        def run():
+            po.srand(20)
+            r = po.RefLib(20, mode)
+            r.L.qc_bernstein_vazirani(r.c, 0x55555 & 0x7FFFF)
+            import ctypes
+            res = (ctypes.c_int * 20)()
+            r.L.qc_measure_all(r.c, res)
+            r.close()
+            return list(res)
+        bits, dt = timed(run)
+        cfg1[f"cpu_{mode}_s"] = dt
+        cfg1[f"cpu_{mode}_bits"] = "".join(map(str, bits))
+    # parity: same seed, same measured bits (sequential reference vs GPU `reference` semantics; the
+    # OpenMP / pthread modes race -- SURVEY section 4 -- and are timing-only)
+    if "cpu_seq_bits" in cfg1:
+        cfg1["bits_match_sequential_reference"] = cfg1["cpu_seq_bits"] == cfg1["gpu_reference_bits"]
+    if "cpu_corrected_bits" in cfg1:
+        cfg1["bits_match_corrected_reference"] = cfg1["cpu_corrected_bits"] == cfg1["gpu_corrected_bits"]
+out["config1_dj20"] = cfg1
+
+# ---------------------------------------------------------------- config 2
+cfg2 = {}
+for sem in ("corrected", "reference"):
+    c = Circuit(24, semantics=sem)
+    c.grover_search(0x0ABCDE); c.flush()                      # warm-up
+    c.close()
+    c = Circuit(24, semantics=sem)
+    c.set_timing(True); c.marker(0)
+    _, dt = timed(lambda: (c.grover_search(0x0ABCDE), c.flush()))
+    c.marker(1)
+    p = c.get_probability(0x0ABCDE); best = c.find_most_likely_state()
+    st = c.stats()
+    cfg2[sem] = {"seconds": dt, "device_ms": c.marker_elapsed_ms(0, 1), "iterations": 3216,
+                 "iterations_per_s": 3216 / dt, "p_solution": p, "argmax": best,
+                 "GBps_48B_per_amp_per_iteration": 3216 * 48 * 2.0 ** 24 / dt / 1e9,
+                 "kernel_launches": st["kernel_launches"]}
+    c.close()
+if not skip_cpu and po.ref_available("seq"):
+    # the reference needs ~0.1 s per iteration at 24 qubits: time 40 iterations' worth of the same
+    # calls (phase flip + diffusion after the 24 Hadamards) and scale
+    r = po.RefLib(24, "seq")
+    for q in range(24):
+        r.h(q)
+    def it():
+        for _ in range(40):
+            r.L.qcsref_phase_flip(r.c, 0x0ABCDE); r.L.qcsref_diffusion(r.c)
+    _, dt = timed(it)
+    r.close()
+    cfg2["cpu_seq"] = {"seconds_per_iteration": dt / 40, "iterations_per_s": 40 / dt,
+                       "estimated_seconds_3216_iterations": dt / 40 * 3216,
+                       "sample": "40 iterations of q_apply_phase_flip + q_apply_diffusion (sequential mode, 1 core)"}
+out["config2_grover24"] = cfg2
+
+# ---------------------------------------------------------------- config 3
+c = Circuit(30, semantics="corrected")
+c.set_timing(True)
+c.qft(); c.flush(); c.reset_stats()
+c.marker(0); c.qft(); c.flush(); c.marker(1)
+ms = c.marker_elapsed_ms(0, 1); st = c.stats()
+# after two QFTs of |0..0>: QFT(uniform) -- spot-check the norm through the exact sequential sum
+out["config3_qft30"] = {"device_ms": ms, "gates_per_s": 465 / (ms * 1e-3), "passes": st["passes"],
+                        "pass_GBps": st["pass_bytes"] / (st["pass_ms"] * 1e-3) / 1e9}
+c.close()
+print(json.dumps(out), flush=True)
