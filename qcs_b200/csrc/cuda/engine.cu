@@ -89,6 +89,9 @@ static int load_options(Options &o) {
   v = option_value("fixed_low");
   if (!v.empty()) o.fixed_low = std::atoi(v.c_str());
   if (o.fixed_low < 1 || o.fixed_low > QCS_LANE_BITS) o.fixed_low = Options().fixed_low;
+  v = option_value("min_fused_victim");
+  if (!v.empty()) o.min_fused_victim = std::atoi(v.c_str());
+  if (o.min_fused_victim < 0 || o.min_fused_victim > QCS_LANE_BITS) o.min_fused_victim = Options().min_fused_victim;
   v = option_value("peephole");
   o.peephole = !(v == "off" || v == "0");
   return QCS_CUDA_OK;
@@ -343,8 +346,14 @@ static int run_local(Engine &e, const std::vector<PhysGate> &gates) {
 // Picks the local position to trade for a global one at queue index `from`: the position whose
 // next use as a pairing target lies farthest ahead.  Among equally idle ones, the one whose last
 // pairing use since `since` lies farthest BACK (the swap may then ride on an earlier pass), then
-// the highest (long contiguous rows stay intact).  Never positions 0..4 (lane bits of every tile).
-static int pick_victim(const Engine &e, const std::vector<HostGate> &q, size_t from, size_t since) {
+// the highest (long contiguous rows stay intact).  Positions below `lowest` are never traded: 5 for
+// stand-alone swaps (positions 0..4 are the 512-byte rows the swap kernels move); option
+// min_fused_victim (2..5) when the swap rides on a pass's stores -- a qubit that arrives at one of
+// the positions every tile contains can be paired in ANY later pass (QFT: the three incoming
+// qubits join the last pass instead of needing one of their own), at the price of 64..256-byte
+// instead of 512-byte remote store runs.
+static int pick_victim(const Engine &e, const std::vector<HostGate> &q, size_t from, size_t since,
+                       int lowest) {
   std::vector<long> next_use(e.nl, (long)q.size() + 1), last_use(e.nl, -1);
   for (size_t i = q.size(); i-- > since;) {
     Classified c = classify_gate(q[i].m, q[i].control >= 0, e.opt.sem);
@@ -356,10 +365,17 @@ static int pick_victim(const Engine &e, const std::vector<HostGate> &q, size_t f
   }
   int best = e.nl - 1;
   long best_next = -1, best_last = 0;
-  for (int pos = e.nl - 1; pos >= QCS_LANE_BITS && pos >= 0; pos--) {
-    if (next_use[pos] > best_next || (next_use[pos] == best_next && last_use[pos] < best_last)) {
+  bool best_low = false;
+  for (int pos = e.nl - 1; pos >= lowest && pos >= 0; pos--) {
+    // positions every tile contains (only offered when lowest < 5) win ties: whatever arrives there
+    // is pairable in every later pass
+    const bool low = pos < QCS_LANE_BITS;
+    if (next_use[pos] > best_next ||
+        (next_use[pos] == best_next &&
+         (last_use[pos] < best_last || (last_use[pos] == best_last && low && !best_low)))) {
       best_next = next_use[pos];
       best_last = last_use[pos];
+      best_low = low;
       best = pos;
     }
   }
@@ -417,7 +433,7 @@ static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, si
     }
     if (x == end) return run_local(e, batch);
     const int gpos = e.perm[q[x].target];
-    const int victim = pick_victim(e, q, x, i);
+    const int victim = pick_victim(e, q, x, i, fuse ? e.opt.min_fused_victim : QCS_LANE_BITS);
     if (!fuse) {
       RC(run_local(e, batch));
       RC(swap_positions(e, victim, gpos));
@@ -508,6 +524,8 @@ static size_t cancel_exact_pairs(std::vector<HostGate> &q) {
   return before - w;
 }
 
+static int canonicalize(Engine &e);
+
 static int flush(Engine &e) {
   if (e.queue.empty()) return QCS_CUDA_OK;
   std::vector<HostGate> q;
@@ -522,6 +540,7 @@ static int flush(Engine &e) {
     // reference's scratch buffer holds the complete pre-gate state.  Execute
     // all but the last gate fused in place, snapshot, then the last gate.
     RC(run_range(e, q, 0, q.size() - 1));
+    if (dist().active) RC(canonicalize(e));  // the snapshot is taken in the identity layout
     RC(ensure_scratch(e));
     if (!e.opt.dryrun) {
       CK(cudaMemcpyAsync(e.scratch, e.live, e.local_size * sizeof(double2),
@@ -578,6 +597,20 @@ static int canonicalize(Engine &e) {
   for (int q = 0; q < e.n; q++)
     if (e.perm[q] != q) return set_error(QCS_CUDA_ERR_CUDA, "internal: layout not canonical");
   return QCS_CUDA_OK;
+}
+
+static bool layout_is_identity(const Engine &e) {
+  for (int q = 0; q < e.n; q++)
+    if (e.perm[q] != q) return false;
+  return true;
+}
+
+// physical basis index (rank bits on top) of logical basis index `index` under the current layout
+static uint64_t physical_index(const Engine &e, uint64_t index) {
+  uint64_t phys = 0;
+  for (int q = 0; q < e.n; q++)
+    if ((index >> q) & 1ull) phys |= 1ull << e.perm[q];
+  return phys;
 }
 
 static int require_data(const Engine &e) {
@@ -842,10 +875,14 @@ int qcs_cuda_phase_flip(qcs_cuda_engine *e, long index) {
   if (index < 0 || (uint64_t)index >= (1ull << e->n))  // reference src/q_gates.c:306-309
     return set_error(QCS_CUDA_ERR_INVALID, "Invalid state or index for phase flip.");
   RC(flush(*e));
-  RC(canonicalize(*e));
+  // reference semantics: the buffers trade roles below, so both must be in the identity layout
+  // (flush snapshots the scratch buffer in it)
+  if (e->opt.sem == SEM_REFERENCE) RC(canonicalize(*e));
   if (e->opt.dryrun) return QCS_CUDA_OK;
-  const bool mine = ((uint64_t)index >> e->nl) == (e->shard_base >> e->nl);
-  const uint64_t local = (uint64_t)index & (e->local_size - 1);
+  // one amplitude: found through the layout, wherever position swaps have left it
+  const uint64_t phys = physical_index(*e, (uint64_t)index);
+  const bool mine = (phys >> e->nl) == (e->shard_base >> e->nl);
+  const uint64_t local = phys & (e->local_size - 1);
   if (e->opt.sem == SEM_REFERENCE) {
     // swap buffers, then live[idx] = -scratch[idx] (reference src/q_gates.c:311-316)
     RC(ensure_scratch(*e));
@@ -959,18 +996,19 @@ int qcs_cuda_get_amplitude(qcs_cuda_engine *e, long index, double out[2]) {
     return set_error(QCS_CUDA_ERR_INVALID, "state index out of range");
   RC(flush(*e));
   RC(require_data(*e));
-  RC(canonicalize(*e));
+  // one amplitude: found through the layout, wherever position swaps have left it
+  const uint64_t phys = physical_index(*e, (uint64_t)index);
   double2 v = make_double2(0.0, 0.0);
-  const bool mine = ((uint64_t)index >> e->nl) == (e->shard_base >> e->nl);
+  const bool mine = (phys >> e->nl) == (e->shard_base >> e->nl);
   if (mine) {
-    CK(cudaMemcpyAsync(&v, e->live + ((uint64_t)index & (e->local_size - 1)), sizeof(v),
+    CK(cudaMemcpyAsync(&v, e->live + (phys & (e->local_size - 1)), sizeof(v),
                        cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
   }
   if (dist().active) {
     std::vector<double2> all(dist().world);
     RC(dist_allgather_host(&v, all.data(), sizeof(v)));
-    v = all[(uint64_t)index >> e->nl];
+    v = all[phys >> e->nl];
   }
   out[0] = v.x;
   out[1] = v.y;
@@ -993,22 +1031,40 @@ int qcs_cuda_argmax(qcs_cuda_engine *e, long *index) {
   if (!e || !index) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
   RC(flush(*e));
   RC(require_data(*e));
-  RC(canonicalize(*e));
-  CK(launch_argmax(e->live, e->local_size, e->ws, e->stream));
+  const bool permuted = !layout_is_identity(*e);
+  if (permuted) {
+    // ties are decided by logical index inside the kernel: no need to restore the layout
+    LogicalIndexLut lut;
+    std::memset(&lut, 0, sizeof(lut));
+    for (int p = e->nl; p < e->n; p++)
+      if ((e->shard_base >> p) & 1ull) lut.base |= 1ull << e->inv_perm[p];
+    for (int byte = 0; byte < 4; byte++)
+      for (int v = 0; v < 256; v++) {
+        unsigned long long l = 0;
+        for (int b = 0; b < 8; b++) {
+          const int p = 8 * byte + b;
+          if (p < e->nl && ((v >> b) & 1)) l |= 1ull << e->inv_perm[p];
+        }
+        lut.t[byte][v] = l;
+      }
+    CK(launch_argmax_permuted(e->live, e->local_size, lut, e->ws, e->stream));
+  } else {
+    CK(launch_argmax(e->live, e->local_size, e->ws, e->stream));
+  }
   e->kernel_launches += 2;
   e->algorithmic_bytes += 16.0 * (double)e->local_size;
   struct { double p; long long idx; } mine{0.0, 0};
   CK(cudaMemcpyAsync(&mine.p, e->ws.result, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaMemcpyAsync(&mine.idx, e->ws.iresult, sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  mine.idx += (long long)e->shard_base;
+  if (!permuted) mine.idx += (long long)e->shard_base;
   if (dist().active) {
     std::vector<decltype(mine)> all(dist().world);
     RC(dist_allgather_host(&mine, all.data(), sizeof(mine)));
     double best_p = 0.0;
     long long best_i = 0;
-    for (auto &c : all)  // ascending rank == ascending index: strict > keeps the first maximum
-      if (c.p > best_p) { best_p = c.p; best_i = c.idx; }
+    for (auto &c : all)  // the first maximum in LOGICAL index order wins (strict >, qcs.c:472)
+      if (c.p > best_p || (c.p == best_p && c.p > 0.0 && c.idx < best_i)) { best_p = c.p; best_i = c.idx; }
     mine.idx = best_i;
   }
   *index = (long)mine.idx;

@@ -20,6 +20,9 @@ struct Options {
   double pass_flops = 1000.0;  // FP64 work per amplitude a pass may fuse; measured flat above ~200 (scripts/budget_sweep.py): a pass costs max(memory, FP64), splitting it never helps
   int exchange = 0;  // 0: NCCL send/recv, 1: peer-memory swap kernel
   int fixed_low = 5;       // positions every tile contains (contiguous global rows of 16 << fixed_low bytes)
+  int min_fused_victim = 5;  // lowest local position a pass-carried swap may trade away (2..5; measured: a
+                             // qubit arriving at an always-in-tile position saves a pass in a QFT but its
+                             // 64..256-byte remote store runs cost 1.5-3 ms per swap: no net gain)
   bool peephole = true;    // drop exactly self-cancelling gate pairs from the queue (corrected semantics)
   bool fuse_swaps = true;  // fold position swaps into the stores of a pass (peer-memory path only)
   int tile_kernel = 3;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8), 3: ldg8 (512 thr x 8 amps, plain loads; default)

@@ -64,6 +64,15 @@ cudaError_t launch_zero_half(double2 *state, uint64_t n_amps, int pos, int keep_
 cudaError_t launch_negate_one(double2 *dst, const double2 *src, uint64_t index, cudaStream_t s);
 cudaError_t launch_argmax(const double2 *state, uint64_t n_amps, ReduceWorkspace &ws,
                           cudaStream_t s);  // result[0] = max prob, iresult[0] = first index
+// Local (physical) index -> logical basis index under the current qubit layout, one table per index
+// byte (shards hold at most 2^32 amplitudes); `base` = the contribution of this rank's bits.
+struct LogicalIndexLut {
+  unsigned long long base;
+  unsigned long long t[4][256];
+};
+// same, ties resolved by LOGICAL index; iresult[0] is a logical (global) index
+cudaError_t launch_argmax_permuted(const double2 *state, uint64_t n_amps,
+                                   const LogicalIndexLut &lut, ReduceWorkspace &ws, cudaStream_t s);
 
 // Exact replay of the reference's left-to-right rounded accumulation of
 // |a_i|^2 (optionally only over indices with bit `mask_pos` clear; -1 = all).

@@ -224,6 +224,46 @@ __global__ void __launch_bounds__(RB) argmax_kernel(const double2 *__restrict__ 
   }
 }
 
+// The same over a shard whose index bits are permuted (multi-GPU layouts after position swaps):
+// candidates are compared by their LOGICAL index, assembled from four byte-indexed tables
+// (LogicalIndexLut, built by the engine from the current layout), so "first maximum wins" holds
+// without restoring the identity layout first.
+__global__ void __launch_bounds__(RB)
+argmax_permuted_kernel(const double2 *__restrict__ state, uint64_t n,
+                       const __grid_constant__ LogicalIndexLut lut, double *partials,
+                       long long *ipartials) {
+  __shared__ unsigned long long tab[4][256];
+  for (int k = threadIdx.x; k < 4 * 256; k += blockDim.x) tab[k >> 8][k & 255] = lut.t[k >> 8][k & 255];
+  __syncthreads();
+  Best b{0.0, 0x7fffffffffffffffll};
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double p = norm_sq(__ldcs(state + i));
+    if (p > 0.0 && p >= b.p) {
+      const long long logical = (long long)(lut.base | tab[0][i & 255] | tab[1][(i >> 8) & 255] |
+                                            tab[2][(i >> 16) & 255] | tab[3][(i >> 24) & 255]);
+      if (p > b.p || logical < b.idx) {
+        b.p = p;
+        b.idx = logical;
+      }
+    }
+  }
+  __shared__ double shp[RB / 32];
+  __shared__ long long shi[RB / 32];
+  b = warp_best(b);
+  if ((threadIdx.x & 31) == 0) {
+    shp[threadIdx.x >> 5] = b.p;
+    shi[threadIdx.x >> 5] = b.idx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Best t{shp[0], shi[0]};
+    for (int w = 1; w < RB / 32; w++) t = better(t, Best{shp[w], shi[w]});
+    partials[blockIdx.x] = t.p;
+    ipartials[blockIdx.x] = t.idx;
+  }
+}
+
 __global__ void argmax_final_kernel(const double *partials, const long long *ipartials, int nb,
                                     double *result, long long *iresult) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -502,6 +542,14 @@ cudaError_t launch_negate_one(double2 *dst, const double2 *src, uint64_t index, 
 cudaError_t launch_argmax(const double2 *state, uint64_t n, ReduceWorkspace &ws, cudaStream_t s) {
   const unsigned nb = grid_for(n, RB * 8);
   argmax_kernel<<<nb, RB, 0, s>>>(state, n, ws.partials, ws.ipartials);
+  argmax_final_kernel<<<1, 32, 0, s>>>(ws.partials, ws.ipartials, (int)nb, ws.result, ws.iresult);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_argmax_permuted(const double2 *state, uint64_t n, const LogicalIndexLut &lut,
+                                   ReduceWorkspace &ws, cudaStream_t s) {
+  const unsigned nb = grid_for(n, RB * 8);
+  argmax_permuted_kernel<<<nb, RB, 0, s>>>(state, n, lut, ws.partials, ws.ipartials);
   argmax_final_kernel<<<1, 32, 0, s>>>(ws.partials, ws.ipartials, (int)nb, ws.result, ws.iresult);
   return cudaGetLastError();
 }
