@@ -528,6 +528,7 @@ static int canonicalize(Engine &e);
 
 static int flush(Engine &e) {
   if (e.queue.empty()) return QCS_CUDA_OK;
+  e.carried_sum_valid = false;  // gates are about to change the amplitudes
   std::vector<HostGate> q;
   q.swap(e.queue);
   e.last_plan.clear();
@@ -688,6 +689,7 @@ static int exact_total(Engine &e, int pos, double *total) {
 }
 
 static int normalize_now(Engine &e) {
+  e.carried_sum_valid = false;
   double total = 0.0;
   RC(exact_total(e, -1, &total));
   // q_state_normalize (reference src/q_utils.c:111-117)
@@ -888,11 +890,12 @@ int qcs_cuda_phase_flip(qcs_cuda_engine *e, long index) {
     RC(ensure_scratch(*e));
     std::swap(e->live, e->scratch);
     if (mine) {
-      CK(launch_negate_one(e->live, e->scratch, local, e->stream));
+      CK(launch_negate_one(e->live, e->scratch, local, nullptr, e->stream));
       e->kernel_launches++;
     }
   } else if (mine) {
-    CK(launch_negate_one(e->live, e->live, local, e->stream));
+    CK(launch_negate_one(e->live, e->live, local,
+                         e->carried_sum_valid ? e->ws.result + RES_LOCAL_SUM_RE : nullptr, e->stream));
     e->kernel_launches++;
   }
   return QCS_CUDA_OK;
@@ -902,19 +905,30 @@ int qcs_cuda_diffusion(qcs_cuda_engine *e) {
   if (!e) return set_error(QCS_CUDA_ERR_INVALID, "null engine");
   RC(flush(*e));
   if (e->opt.dryrun) return QCS_CUDA_OK;
-  CK(launch_complex_sum(e->live, e->local_size, e->ws, e->stream));
-  if (dist().active) RC(dist_allreduce_sum(*e, e->ws.result + RES_SUM_RE, 2));
+  double *res = e->ws.result;
+  // sum of all amplitudes: carried over from the previous diffusion's write pass when nothing but
+  // phase flips touched the state since (Grover's loop), else one read pass
+  if (!e->carried_sum_valid) {
+    CK(launch_complex_sum(e->live, e->local_size, e->ws, e->stream));
+    e->kernel_launches += 2;
+    e->algorithmic_bytes += 16.0 * (double)e->local_size;
+  }
+  CK(cudaMemcpyAsync(res + RES_SUM_RE, res + RES_LOCAL_SUM_RE, 2 * sizeof(double),
+                     cudaMemcpyDeviceToDevice, e->stream));
+  if (dist().active) RC(dist_allreduce_sum(*e, res + RES_SUM_RE, 2));
   CK(launch_diffusion_mean(e->ws, e->opt.sem == SEM_CORRECTED, (double)(1ull << e->n), e->stream));
   if (e->opt.sem == SEM_REFERENCE) {
     // new values go to the other buffer, then the buffers trade roles (:348-355)
     RC(ensure_scratch(*e));
     CK(launch_diffusion_write(e->live, e->scratch, e->local_size, e->ws, e->stream));
     std::swap(e->live, e->scratch);
+    e->kernel_launches += 2;
   } else {
-    CK(launch_diffusion_write(e->live, e->live, e->local_size, e->ws, e->stream));
+    CK(launch_diffusion_write_sum(e->live, e->live, e->local_size, e->ws, e->stream));
+    e->carried_sum_valid = true;
+    e->kernel_launches += 3;
   }
-  e->kernel_launches += 4;
-  e->algorithmic_bytes += 48.0 * (double)e->local_size;
+  e->algorithmic_bytes += 32.0 * (double)e->local_size;
   return QCS_CUDA_OK;
 }
 
@@ -983,6 +997,7 @@ int qcs_cuda_write_amplitudes(qcs_cuda_engine *e, int which, long first, long co
       (uint64_t)first + (uint64_t)count > base + e->local_size)
     return set_error(QCS_CUDA_ERR_INVALID, "amplitude range is not inside this rank's shard");
   if (which) RC(ensure_scratch(*e));
+  e->carried_sum_valid = false;
   double2 *dst = which ? e->scratch : e->live;
   CK(cudaMemcpyAsync(dst + ((uint64_t)first - base), in, (size_t)count * sizeof(double2),
                      cudaMemcpyHostToDevice, e->stream));

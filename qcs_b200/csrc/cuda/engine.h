@@ -54,6 +54,7 @@ struct Engine {
   uint32_t *tile_flags = nullptr;         // one word per tile: handshake of passes that swap on the way out
   std::vector<uint32_t *> peer_flags;     // every rank's tile_flags, peer-mapped
   uint32_t swap_epoch = 0;
+  bool carried_sum_valid = false;  // ws.result[RES_LOCAL_SUM_*] holds the sum of this shard's amplitudes
   ReduceWorkspace ws{};
   void *ws_slab = nullptr;       // one allocation backing every array of ws
   size_t ws_slab_bytes = 0;

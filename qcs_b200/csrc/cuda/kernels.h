@@ -51,17 +51,22 @@ enum { REDUCE_MAX_BLOCKS = 4096, SEQ_CHUNK = 1024 };
 
 cudaError_t launch_init_state(double2 *state, uint64_t n_amps, bool set_one, cudaStream_t s);
 cudaError_t launch_complex_sum(const double2 *state, uint64_t n_amps, ReduceWorkspace &ws,
-                               cudaStream_t s);  // result[0..1] = sum re, sum im
-// result[0..1] (raw sum) -> result[2..3] = 2*mean, per semantics (device-side, no host sync)
+                               cudaStream_t s);  // result[RES_LOCAL_SUM_RE..IM] = this shard's sum
+// result[0..1] (raw sum of the whole state) -> result[2..3] = 2*mean, per semantics (device-side, no host sync)
 cudaError_t launch_diffusion_mean(ReduceWorkspace &ws, bool corrected, double n_total,
                                   cudaStream_t s);
 // dst[i] = 2*mean - src[i]   (dst may alias src)
 cudaError_t launch_diffusion_write(const double2 *src, double2 *dst, uint64_t n_amps,
                                    const ReduceWorkspace &ws, cudaStream_t s);
+// the same and result[RES_LOCAL_SUM_RE..IM] = sum of the values written (carried to the next iteration)
+cudaError_t launch_diffusion_write_sum(const double2 *src, double2 *dst, uint64_t n_amps,
+                                       ReduceWorkspace &ws, cudaStream_t s);
 cudaError_t launch_scale(double2 *state, uint64_t n_amps, double factor, cudaStream_t s);
 cudaError_t launch_zero_half(double2 *state, uint64_t n_amps, int pos, int keep_bit,
                              cudaStream_t s);
-cudaError_t launch_negate_one(double2 *dst, const double2 *src, uint64_t index, cudaStream_t s);
+// dst[index] = -src[index]; carried_sum (device, may be null) -= 2 * src[index]
+cudaError_t launch_negate_one(double2 *dst, const double2 *src, uint64_t index,
+                              double *carried_sum, cudaStream_t s);
 cudaError_t launch_argmax(const double2 *state, uint64_t n_amps, ReduceWorkspace &ws,
                           cudaStream_t s);  // result[0] = max prob, iresult[0] = first index
 // Local (physical) index -> logical basis index under the current qubit layout, one table per index
@@ -82,7 +87,8 @@ cudaError_t launch_argmax_permuted(const double2 *state, uint64_t n_amps,
 //   launch_chunk_resolve K4: exact walk from *exact_start_dev; chunk_exact[k] = running sum
 //                        before chunk k (k = 0..n_chunks), result[RES_EXACT_TOTAL] = after the shard
 enum { RES_SUM_RE = 0, RES_SUM_IM = 1, RES_TWO_MEAN_RE = 2, RES_TWO_MEAN_IM = 3,
-       RES_APPROX_TOTAL = 4, RES_EXACT_TOTAL = 5, RES_ZERO = 6, RES_START = 7, RES_COUNT = 16 };
+       RES_APPROX_TOTAL = 4, RES_EXACT_TOTAL = 5, RES_ZERO = 6, RES_START = 7,
+       RES_LOCAL_SUM_RE = 9, RES_LOCAL_SUM_IM = 10, RES_COUNT = 16 };
 cudaError_t launch_chunk_sums(const double2 *state, uint64_t n_amps, int mask_pos,
                               ReduceWorkspace &ws, cudaStream_t s);
 cudaError_t launch_chunk_deltas(const double2 *state, uint64_t n_amps, int mask_pos,

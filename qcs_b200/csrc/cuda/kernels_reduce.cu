@@ -154,6 +154,42 @@ diffusion_write_kernel(const double2 *src, double2 *dst, uint64_t n,
   }
 }
 
+// The same write, also summing the values it writes (per-block partial sums): the next Grover
+// iteration's mean then needs no read pass of its own -- 32 instead of 48 bytes per amplitude per
+// iteration.  (The reference sums sequentially, src/q_gates.c:334-336; this sum, like
+// complex_sum_kernel's, is a tree: Grover parity is stated to 1e-12, not bit-exact.)
+__global__ void __launch_bounds__(RB)
+diffusion_write_sum_kernel(const double2 *src, double2 *dst, uint64_t n,
+                           const double *__restrict__ two_mean, double *partials) {
+  const double tr = two_mean[0], ti = two_mean[1];
+  double sr = 0.0, si = 0.0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double2 a = __ldcs(src + i);
+    const double2 v = make_double2(__dsub_rn(tr, a.x), __dsub_rn(ti, a.y));
+    __stcs(dst + i, v);
+    sr += v.x;
+    si += v.y;
+  }
+  __shared__ double sh[2][RB / 32];
+  sr = warp_sum(sr);
+  si = warp_sum(si);
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = sr;
+    sh[1][threadIdx.x >> 5] = si;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tr2 = 0.0, ti2 = 0.0;
+    for (int w = 0; w < RB / 32; w++) {
+      tr2 += sh[0][w];
+      ti2 += sh[1][w];
+    }
+    partials[2 * blockIdx.x] = tr2;
+    partials[2 * blockIdx.x + 1] = ti2;
+  }
+}
+
 __global__ void __launch_bounds__(256) scale_kernel(double2 *state, uint64_t n, double f) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -172,9 +208,16 @@ zero_half_kernel(double2 *state, uint64_t n_items, int pos, uint64_t zero_bit) {
   }
 }
 
-__global__ void negate_one_kernel(double2 *dst, const double2 *src, uint64_t index) {
+// carried_sum (may be null): running sum of all amplitudes kept across Grover iterations; negating
+// one amplitude takes it out twice
+__global__ void negate_one_kernel(double2 *dst, const double2 *src, uint64_t index,
+                                  double *carried_sum) {
   const double2 a = src[index];
   dst[index] = make_double2(-a.x, -a.y);
+  if (carried_sum) {
+    carried_sum[0] = (carried_sum[0] - a.x) - a.x;
+    carried_sum[1] = (carried_sum[1] - a.y) - a.y;
+  }
 }
 
 // ---------------------------------------------------------------- argmax
@@ -506,13 +549,21 @@ cudaError_t launch_complex_sum(const double2 *state, uint64_t n, ReduceWorkspace
                                cudaStream_t s) {
   const unsigned nb = grid_for(n, RB * 8);
   complex_sum_kernel<<<nb, RB, 0, s>>>(state, n, ws.partials);
-  complex_sum_final_kernel<<<1, 1024, 0, s>>>(ws.partials, (int)nb, ws.result);
+  complex_sum_final_kernel<<<1, 1024, 0, s>>>(ws.partials, (int)nb, ws.result + RES_LOCAL_SUM_RE);
   return cudaGetLastError();
 }
 
 cudaError_t launch_diffusion_mean(ReduceWorkspace &ws, bool corrected, double n_total,
                                   cudaStream_t s) {
   diffusion_mean_kernel<<<1, 1, 0, s>>>(ws.result, corrected ? 1 : 0, n_total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_diffusion_write_sum(const double2 *src, double2 *dst, uint64_t n,
+                                       ReduceWorkspace &ws, cudaStream_t s) {
+  const unsigned nb = grid_for(n, RB * 8);
+  diffusion_write_sum_kernel<<<nb, RB, 0, s>>>(src, dst, n, ws.result + 2, ws.partials);
+  complex_sum_final_kernel<<<1, 1024, 0, s>>>(ws.partials, (int)nb, ws.result + RES_LOCAL_SUM_RE);
   return cudaGetLastError();
 }
 
@@ -534,8 +585,9 @@ cudaError_t launch_zero_half(double2 *state, uint64_t n, int pos, int keep_bit, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_negate_one(double2 *dst, const double2 *src, uint64_t index, cudaStream_t s) {
-  negate_one_kernel<<<1, 1, 0, s>>>(dst, src, index);
+cudaError_t launch_negate_one(double2 *dst, const double2 *src, uint64_t index,
+                              double *carried_sum, cudaStream_t s) {
+  negate_one_kernel<<<1, 1, 0, s>>>(dst, src, index, carried_sum);
   return cudaGetLastError();
 }
 
