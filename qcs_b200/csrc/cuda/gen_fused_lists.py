@@ -207,15 +207,24 @@ def emit(R):
         if t < 0:  # the target is a thread-level bit too: all or none of this thread's amplitudes
             body += [f"ld.param.u8 cs, [%1+{OFF_TPOS}];", "shr.u64 t64, %2, cs;", "and.b64 t64, t64, 1;",
                      "setp.eq.u64 p, t64, 0;", "@p mov.u32 mask, 0;"]
+        diag_regs = regs(R, t, 1) if t >= 0 else regs(R)
+        entry = ["bfind.u32 kidx, low;", f"mul.wide.u32 ea, kidx, {E};", "add.u64 ea, ea, %1;",
+                 f"ld.param.v2.f64 {{dr, di}}, [ea+{E + OFF_M(6)}];"]
+        for r in diag_regs:
+            entry += op_diag(r)
         body += ["redux.sync.or.b32 wm, mask, 0xffffffff;",
+                 # all lanes of the warp take part in the same entries (controls on warp bits or
+                 # outside the tile: the common case): no per-entry lane test, no reconvergence
+                 "setp.eq.u32 pa, mask, wm;", "vote.sync.all.pred pa, pa, 0xffffffff;", f"@pa bra FU{n};",
                  f"FL{n}:", "setp.eq.u32 p, wm, 0;", f"@p bra FE{n};",
                  "neg.s32 low, wm;", "and.b32 low, low, wm;", "xor.b32 wm, wm, low;",
-                 "and.b32 tst, mask, low;", "setp.eq.u32 pa, tst, 0;", f"@pa bra FS{n};",
-                 "bfind.u32 kidx, low;", f"mul.wide.u32 ea, kidx, {E};", "add.u64 ea, ea, %1;",
-                 f"ld.param.f64 dr, [ea+{E + OFF_M(6)}];", f"ld.param.f64 di, [ea+{E + OFF_M(7)}];"]
-        for r in (regs(R, t, 1) if t >= 0 else regs(R)):
-            body += op_diag(r)
+                 "and.b32 tst, mask, low;", "setp.eq.u32 pa, tst, 0;", f"@pa bra FS{n};"]
+        body += entry
         body += [f"FS{n}:", f"bra FL{n};",
+                 f"FU{n}:", "setp.eq.u32 p, wm, 0;", f"@p bra FE{n};",
+                 "neg.s32 low, wm;", "and.b32 low, low, wm;", "xor.b32 wm, wm, low;"]
+        body += entry
+        body += [f"bra.uni FU{n};",
                  f"FE{n}:", "add.s32 %0, %0, K;", "bra DONE;",
                  # controls at arbitrary positions: gather the mask from the entries' cpos bytes
                  f"FG{n}:", "mov.u32 mask, 0;", "mov.u32 kidx, 0;", "mov.u64 ea, %1;",
