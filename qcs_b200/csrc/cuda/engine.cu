@@ -774,7 +774,9 @@ int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
     const size_t sz[] = {up(4 * REDUCE_MAX_BLOCKS * sizeof(double)), up(REDUCE_MAX_BLOCKS * sizeof(long long)),
                          up(RES_COUNT * sizeof(double)), up(4 * sizeof(long long)),
                          up(n_chunks * sizeof(double)), up((n_chunks + 1) * sizeof(double)),
-                         up(n_chunks * sizeof(double)), up(n_chunks), up((n_chunks + 1) * sizeof(double))};
+                         up(n_chunks * sizeof(double)), up(n_chunks), up((n_chunks + 1) * sizeof(double)),
+                         up((n_chunks / 1024 + 2) * sizeof(double)), up((n_chunks / 1024 + 2) * sizeof(double)),
+                         up(n_chunks / 1024 + 2)};
     size_t total = 0;
     for (size_t b : sz) total += b;
     e->ws_slab_bytes = total;
@@ -788,7 +790,10 @@ int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
     ws.chunk_approx = (double *)p; p += sz[5];
     ws.chunk_delta = (double *)p; p += sz[6];
     ws.chunk_flag = (unsigned char *)p; p += sz[7];
-    ws.chunk_exact = (double *)p;
+    ws.chunk_exact = (double *)p; p += sz[8];
+    ws.group_sum = (double *)p; p += sz[9];
+    ws.group_exact = (double *)p; p += sz[10];
+    ws.group_flag = (unsigned char *)p;
   }
   if ((rc = check_cuda(cudaMemsetAsync(ws.result, 0, RES_COUNT * sizeof(double), e->stream), "cudaMemset")))
     return fail(rc);

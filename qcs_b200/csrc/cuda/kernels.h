@@ -45,6 +45,9 @@ struct ReduceWorkspace {
   double *chunk_delta;     // device, n_chunks
   unsigned char *chunk_flag;  // device, n_chunks
   double *chunk_exact;     // device, n_chunks + 1
+  double *group_sum;       // device, n_chunks / 1024 + 1 (two-level resolve of large shards)
+  double *group_exact;     // device, n_chunks / 1024 + 1
+  unsigned char *group_flag;  // device, n_chunks / 1024 + 1
   size_t n_chunks_cap;
 };
 enum { REDUCE_MAX_BLOCKS = 4096, SEQ_CHUNK = 1024 };

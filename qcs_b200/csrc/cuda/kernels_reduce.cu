@@ -441,27 +441,63 @@ __device__ __forceinline__ double replay_chunk(const double2 *__restrict__ state
   return S;
 }
 
-// K4: walk the chunks in order (one warp; every lane carries the same S).
-__global__ void __launch_bounds__(32)
-chunk_resolve_kernel(const double2 *__restrict__ state, uint64_t n_amps, uint64_t n_chunks,
-                     uint64_t chunk_len, int mask_pos, const double *start_dev,
-                     const double *__restrict__ approx, const double *__restrict__ delta,
-                     const unsigned char *__restrict__ flag, int have_deltas,
-                     double *__restrict__ exact, double *total_out, long long *replays) {
-  const int lane = threadIdx.x;
-  double S = *start_dev;
-  long long n_replay = 0;
-  for (uint64_t base = 0; base < n_chunks; base += 32) {
+// ---- K4, two levels (shards with many chunks) ---------------------------------------------
+// A one-warp walk over 2^20 chunks (30 qubits) costs ~100 ms.  The shortcut the walk takes per chunk
+// composes: while nothing is flagged and the running sum stays in one binade, every step is an
+// EXACT addition of a multiple of that binade's quantum, so a whole group of chunks advances the
+// sum by the exact total of its increments.  K4a sums the increments of each group of
+// RESOLVE_GROUP chunks in parallel and marks groups that contain a flagged chunk or span a binade
+// of the approximate prefix; K4b walks the (few) groups, falling back to the per-chunk walk inside
+// marked groups or when the running sum leaves the binade; K4c fills the per-chunk running sums
+// of the clean groups in parallel (the sampler needs them).
+constexpr int RESOLVE_GROUP = 1024;
+
+__global__ void __launch_bounds__(256)
+group_sum_kernel(const double *__restrict__ delta, const double *__restrict__ approx,
+                 const unsigned char *__restrict__ flag, uint64_t n_chunks, uint64_t n_groups,
+                 double *__restrict__ gsum, unsigned char *__restrict__ gflag) {
+  const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_groups) return;
+  const uint64_t first = g * RESOLVE_GROUP;
+  const uint64_t last = first + RESOLVE_GROUP < n_chunks ? first + RESOLVE_GROUP : n_chunks;
+  double s = 0.0;
+  int f = 0;
+  for (uint64_t c = first + lane; c < last; c += 32) {
+    const int fc = flag[c];
+    f |= fc;
+    if (!(fc & FLAG_ZERO)) s += delta[c];  // exact: multiples of one quantum, total below the binade's top
+  }
+  s = warp_sum(s);
+  f = __reduce_or_sync(0xffffffffu, f);
+  if (lane == 0) {
+    unsigned char out = 0;
+    if (f & (FLAG_TIE | FLAG_CROSS)) out = 1;
+    if (exponent_of(approx[first]) != exponent_of(approx[last - 1])) out = 1;
+    gsum[g] = s;
+    gflag[g] = out;
+  }
+}
+
+// the per-chunk walk over chunks [c_begin, c_end), shared by the one-level kernel and K4b
+__device__ __forceinline__ double walk_chunks(const double2 *__restrict__ state, uint64_t c_begin,
+                                              uint64_t c_end, uint64_t chunk_len, int mask_pos,
+                                              const double *__restrict__ approx,
+                                              const double *__restrict__ delta,
+                                              const unsigned char *__restrict__ flag,
+                                              int have_deltas, double *__restrict__ exact, double S,
+                                              int lane, long long &n_replay) {
+  for (uint64_t base = c_begin; base < c_end; base += 32) {
     const uint64_t mine = base + lane;
     double my_d = 0.0, my_a = 0.0;
     int my_f = FLAG_CROSS;
-    if (have_deltas && mine < n_chunks) {
+    if (have_deltas && mine < c_end) {
       my_d = delta[mine];
       my_a = approx[mine];
       my_f = flag[mine];
     }
     double my_exact = 0.0;
-    const int lim = (int)((n_chunks - base) < 32 ? (n_chunks - base) : 32);
+    const int lim = (int)((c_end - base) < 32 ? (c_end - base) : 32);
     for (int j = 0; j < lim; j++) {
       const double d = __shfl_sync(0xffffffffu, my_d, j);
       const double a = __shfl_sync(0xffffffffu, my_a, j);
@@ -481,8 +517,87 @@ chunk_resolve_kernel(const double2 *__restrict__ state, uint64_t n_amps, uint64_
         n_replay++;
       }
     }
-    if (mine < n_chunks) exact[mine] = my_exact;
+    if (mine < c_end) exact[mine] = my_exact;
   }
+  return S;
+}
+
+// K4b: one warp walks the groups; gexact[g] = running sum before group g, or NaN-free marker
+// gdone[g] = 1 when the per-chunk walk already wrote that group's chunk_exact entries.
+__global__ void __launch_bounds__(32)
+group_resolve_kernel(const double2 *__restrict__ state, uint64_t n_chunks, uint64_t n_groups,
+                     uint64_t chunk_len, int mask_pos, const double *start_dev,
+                     const double *__restrict__ approx, const double *__restrict__ delta,
+                     const unsigned char *__restrict__ flag, const double *__restrict__ gsum,
+                     unsigned char *__restrict__ gflag, double *__restrict__ gexact,
+                     double *__restrict__ exact, double *total_out, long long *replays) {
+  const int lane = threadIdx.x;
+  double S = *start_dev;
+  long long n_replay = 0;
+  for (uint64_t g = 0; g < n_groups; g++) {
+    const uint64_t first = g * RESOLVE_GROUP;
+    const uint64_t last = first + RESOLVE_GROUP < n_chunks ? first + RESOLVE_GROUP : n_chunks;
+    bool clean = gflag[g] == 0 && exponent_of(S) == exponent_of(approx[first]);
+    double Snew = S;
+    if (clean) {
+      Snew = __dadd_rn(S, gsum[g]);
+      clean = exponent_of(Snew) == exponent_of(S);
+    }
+    if (lane == 0) gexact[g] = S;
+    if (clean) {
+      S = Snew;  // K4c fills this group's chunk_exact entries
+    } else {
+      S = walk_chunks(state, first, last, chunk_len, mask_pos, approx, delta, flag, 1, exact, S, lane,
+                      n_replay);
+      if (lane == 0) gflag[g] = 2;  // done here
+    }
+  }
+  if (lane == 0) {
+    exact[n_chunks] = S;
+    *total_out = S;
+    if (replays) *replays = n_replay;
+  }
+}
+
+// K4c: exact[c] = gexact[g] + (increments of the group's earlier chunks) for the clean groups.
+__global__ void __launch_bounds__(256)
+group_fill_kernel(const double *__restrict__ delta, const unsigned char *__restrict__ flag,
+                  uint64_t n_chunks, uint64_t n_groups, const unsigned char *__restrict__ gflag,
+                  const double *__restrict__ gexact, double *__restrict__ exact) {
+  const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_groups || gflag[g] == 2) return;
+  const uint64_t first = g * RESOLVE_GROUP;
+  const uint64_t last = first + RESOLVE_GROUP < n_chunks ? first + RESOLVE_GROUP : n_chunks;
+  // lane l owns chunks [first + 32 l, first + 32 l + 32)
+  const uint64_t lo = first + (uint64_t)lane * (RESOLVE_GROUP / 32);
+  double mine = 0.0;
+  for (uint64_t c = lo; c < lo + RESOLVE_GROUP / 32 && c < last; c++)
+    if (!(flag[c] & FLAG_ZERO)) mine += delta[c];
+  double incl = mine;  // inclusive scan over lanes (exact additions, any order)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  double run = gexact[g] + (incl - mine);
+  for (uint64_t c = lo; c < lo + RESOLVE_GROUP / 32 && c < last; c++) {
+    exact[c] = run;
+    if (!(flag[c] & FLAG_ZERO)) run += delta[c];
+  }
+}
+
+// K4 (one level): walk the chunks in order (one warp; every lane carries the same S).
+__global__ void __launch_bounds__(32)
+chunk_resolve_kernel(const double2 *__restrict__ state, uint64_t n_amps, uint64_t n_chunks,
+                     uint64_t chunk_len, int mask_pos, const double *start_dev,
+                     const double *__restrict__ approx, const double *__restrict__ delta,
+                     const unsigned char *__restrict__ flag, int have_deltas,
+                     double *__restrict__ exact, double *total_out, long long *replays) {
+  const int lane = threadIdx.x;
+  long long n_replay = 0;
+  const double S = walk_chunks(state, 0, n_chunks, chunk_len, mask_pos, approx, delta, flag,
+                               have_deltas, exact, *start_dev, lane, n_replay);
   if (lane == 0) {
     exact[n_chunks] = S;
     *total_out = S;
@@ -641,10 +756,23 @@ cudaError_t launch_chunk_resolve(const double2 *state, uint64_t n, int mask_pos,
     return cudaGetLastError();
   }
   const uint64_t n_chunks = n / SEQ_CHUNK;
-  chunk_resolve_kernel<<<1, 32, 0, s>>>(state, n, n_chunks, SEQ_CHUNK, mask_pos, exact_start_dev,
-                                        ws.chunk_approx, ws.chunk_delta, ws.chunk_flag, 1,
-                                        ws.chunk_exact, ws.result + RES_EXACT_TOTAL,
-                                        ws.iresult + 1);
+  if (n_chunks < 4 * (uint64_t)RESOLVE_GROUP) {
+    chunk_resolve_kernel<<<1, 32, 0, s>>>(state, n, n_chunks, SEQ_CHUNK, mask_pos, exact_start_dev,
+                                          ws.chunk_approx, ws.chunk_delta, ws.chunk_flag, 1,
+                                          ws.chunk_exact, ws.result + RES_EXACT_TOTAL,
+                                          ws.iresult + 1);
+    return cudaGetLastError();
+  }
+  const uint64_t n_groups = (n_chunks + RESOLVE_GROUP - 1) / RESOLVE_GROUP;
+  const unsigned blocks = (unsigned)((n_groups + 7) / 8);  // 8 warps per block, one group per warp
+  group_sum_kernel<<<blocks, 256, 0, s>>>(ws.chunk_delta, ws.chunk_approx, ws.chunk_flag, n_chunks,
+                                          n_groups, ws.group_sum, ws.group_flag);
+  group_resolve_kernel<<<1, 32, 0, s>>>(state, n_chunks, n_groups, SEQ_CHUNK, mask_pos,
+                                        exact_start_dev, ws.chunk_approx, ws.chunk_delta,
+                                        ws.chunk_flag, ws.group_sum, ws.group_flag, ws.group_exact,
+                                        ws.chunk_exact, ws.result + RES_EXACT_TOTAL, ws.iresult + 1);
+  group_fill_kernel<<<blocks, 256, 0, s>>>(ws.chunk_delta, ws.chunk_flag, n_chunks, n_groups,
+                                           ws.group_flag, ws.group_exact, ws.chunk_exact);
   return cudaGetLastError();
 }
 

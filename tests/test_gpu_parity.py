@@ -154,7 +154,7 @@ def test_grover_within_tolerance(n, sem):
     orc.close(); c.close()
 
 
-@pytest.mark.parametrize("n", [3, 9, 10, 11, 13, 16, 20])
+@pytest.mark.parametrize("n", [3, 9, 10, 11, 13, 16, 20, 23])
 def test_exact_sequential_sums(n):
     """prob_0 and the normalisation total are the reference's left-to-right rounded sums, bit for bit."""
     rng = np.random.default_rng(50 + n)
@@ -176,6 +176,29 @@ def test_exact_sequential_sums(n):
             want = po.Oracle.lib().orc_prob0(orc.h_, q)
             assert c.prob0(q) == want, (kind, q, c.prob0(q), want)
         orc.normalize(); c.normalize()
+        assert _same(c.state(), orc.state()), kind
+        orc.close(); c.close()
+
+
+def test_two_level_prefix_resolve_shots_and_collapse():
+    """Shards above 2^22 amplitudes resolve the exact running sum in two levels (groups of 1024
+    chunks, kernels_reduce.cu K4a-c): shots, prob_0 and collapses must still be the reference's,
+    on states whose running sum crosses many binades (skewed), has exact zeros (sparse) and ties."""
+    n = 23
+    rng = np.random.default_rng(2300)
+    states = {
+        "skewed": (rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)) * np.exp(rng.uniform(-40, 2, size=2 ** n)),
+        "uniform": np.full(2 ** n, 2.0 ** (-n / 2), complex),          # every addition is a potential tie
+        "half_zero": np.where(np.arange(2 ** n) % 3 == 0, 0.0, 1.0) * (rng.normal(size=2 ** n) + 0j),
+    }
+    for kind, init in states.items():
+        init = init / np.linalg.norm(init)
+        orc = po.Oracle(n, "corrected"); c = Circuit(n, semantics="corrected")
+        orc.load_state(init); c.load_state(init)
+        po.srand(77); want_sh = orc.run_shots(64); want_m = [orc.measure(n - 1), orc.measure(0), orc.measure(11)]
+        po.srand(77); got = c.run_shots_sparse(64); got_m = [c.measure(n - 1), c.measure(0), c.measure(11)]
+        assert np.array_equal(np.bincount(got[got >= 0], minlength=2 ** n), want_sh), kind
+        assert got_m == want_m, kind
         assert _same(c.state(), orc.state()), kind
         orc.close(); c.close()
 
