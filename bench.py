@@ -136,7 +136,7 @@ def run_reference_sample(n_target: int, budget_s: float = 20.0) -> dict:
     per_gate_est = 6.0 * 2.0 ** (n - 30)  # s, survey-time single-core figure
     n_gates = max(3, min(24, int(budget_s / max(per_gate_est, 1e-3))))
     out = {}
-    for mode in ("seq", "omp"):
+    for mode in ("seq", "simd", "omp"):   # the reference's sequential, QCS_SIMD_ONLY and QCS_CPU_OPENMP builds
         if not po.ref_available(mode):
             continue
         if mode == "omp":
@@ -157,7 +157,7 @@ def run_reference_sample(n_target: int, budget_s: float = 20.0) -> dict:
         dt = time.perf_counter() - t0
         ref.close()
         out[mode] = {"gates": done, "seconds": dt, "gates_per_s_at_sample_width": done / dt,
-                     "gates_per_s": done / dt * scale, "threads": 1 if mode == "seq" else cores}
+                     "gates_per_s": done / dt * scale, "threads": cores if mode == "omp" else 1}
     best = max(out, key=lambda m: out[m]["gates_per_s"])
     return {"value": out[best]["gates_per_s"], "unit": "gates/s",
             "cores": out[best]["threads"], "kind": "reference",
@@ -366,6 +366,9 @@ def main() -> None:
     aux = None
     if (world > 1 or args.aux) and not args.skip_aux:
         aux = random_circuit_aux(Circuit, kw, world, barrier, dist, torch)
+    light = None
+    if world == 1 and not args.skip_aux:
+        light = light_pass_aux(Circuit, kw, n)
 
     if rank != 0:
         if world > 1:
@@ -430,6 +433,8 @@ def main() -> None:
     }
     if aux:
         line["aux_random_circuit"] = aux
+    if light:
+        line["aux_bandwidth_bound_passes"] = light
     if world == 1 and not args.skip_cpu_baseline:
         try:
             line["cpu_baseline"] = {k: v for k, v in run_reference_sample(n, 20.0).items()
@@ -446,6 +451,32 @@ def main() -> None:
 # dram__bytes_read.sum + dram__bytes_write.sum per fused-pass launch, from the ncu --set full
 # captures committed under profiles/ (keyed by local qubits); None where not captured.
 NCU_TRAFFIC_BYTES_PER_LAUNCH = {28: 8.53e9, 30: 34.30e9}  # profiles/r1g_qft30_ldg8_summary.csv
+
+
+def light_pass_aux(Circuit, kw, n) -> dict:
+    """The same kernel on passes that carry little arithmetic: how close a fused pass gets to the
+    HBM roofline when FP64 issue is not the limiter (the headline QFT passes fuse ~190 separately
+    rounded FP64 operations per amplitude; these fuse 4 - 48)."""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else HBM_FALLBACK_GBS
+    out = {}
+    cases = {"one_H_per_pass": ([("h", 8)], {}),
+             "H_on_every_qubit": ([("h", q) for q in range(n)], {}),
+             "QFT_cut_at_48_flops_per_pass": ([("qft",)], {"pass_flops": 48.0})}
+    from oracle.pyoracle import replay
+    for name, (script, extra) in cases.items():
+        k = dict(kw); k.update(extra)
+        c = Circuit(n, **k)
+        c.set_timing(True)
+        replay(c, script); c.flush(); c.reset_stats()
+        for _ in range(3):
+            replay(c, script); c.flush()
+        st = c.stats()
+        c.close()
+        gbs = st["pass_bytes"] / (st["pass_ms"] * 1e-3) / 1e9
+        out[name] = {"passes": st["passes"] // 3, "gates": st["gates_submitted"] // 3,
+                     "ms": st["pass_ms"] / 3, "GBps_per_pass": gbs, "frac_of_hbm_peak": gbs / peak}
+    return out
 
 
 def random_circuit_aux(Circuit, kw, world, barrier, dist, torch) -> dict:
