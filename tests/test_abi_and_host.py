@@ -162,3 +162,22 @@ def test_single_header_bundle_compiles_as_c89(tmp_path):
         assert "no device" in r.stdout and "Error" in r.stderr
     else:
         assert r.stdout.split()[0] == "2"
+
+
+def test_bench_reference_arm_contract_line():
+    """bench.py --impl reference runs on the host cores (no GPU): one JSON line on stdout with the
+    contract keys, the unmodified reference (oracle/_ref) or the C port as the timed thing."""
+    import json, subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                        "--qubits", "16", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                "higher_is_better", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "gates/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
