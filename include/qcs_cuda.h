@@ -102,6 +102,7 @@ int qcs_cuda_write_amplitudes(qcs_cuda_engine *e, int which, long first,
 /* Keys: "semantics" = reference|corrected, "fusion" = on|off,
  * "dryrun" = 0|1, "pass_flops" = <float>, "tile_kernel" = ldg8|ldg|tma|tma16,
  * "exchange" = p2p|nccl (multi-GPU position swaps: in-place peer-memory kernel, or NCCL send/recv),
+ * "tile_bits" = 10|11|12 (largest tile of a fused pass, default 11; a pass runs on the smallest tile that holds its pairing qubits),
  * "peephole" = on|off (corrected semantics: drop exactly self-cancelling X/Y/Z/CNOT/CZ pairs from the queue),
  * "fuse_swaps" = on|off (p2p only: a swap rides on the stores of a fused pass instead of a kernel of its own).
  * Defaults come from QCS_CUDA_<KEY> in the environment; set_default applies

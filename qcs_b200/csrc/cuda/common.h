@@ -5,8 +5,8 @@
 //   shard       the 2^nl amplitudes this rank holds (nl = local qubits)
 //   position    a bit of the physical basis index; positions < nl are local,
 //               positions >= nl are the rank's bits (global)
-//   tile        2^QCS_TILE_BITS amplitudes one CTA holds in registers during a
-//               pass; its index bits are `tile_pos` (always contains 0..4)
+//   tile        2^T amplitudes (T = 10, 11 or 12, chosen per pass) one CTA holds in
+//               registers during a pass; its index bits are `tile_pos` (always contains 0..4)
 //   pass        one fused kernel launch: every amplitude is read once and
 //               written once, a run of gates is applied in between
 //   segment     a stretch of a pass during which the assignment of tile bits
@@ -16,7 +16,11 @@
 #pragma once
 #include <stdint.h>
 
-#define QCS_TILE_BITS 12     // 4096 amplitudes = 64 KiB per tile
+#define QCS_TILE_BITS 12     // largest tile: 4096 amplitudes = 64 KiB (array bounds)
+#define QCS_MIN_TILE_BITS 10 // smallest tile: 1024 amplitudes = 16 KiB.  Smaller tiles mean more CTAs per SM
+                             // (2 / 4 / 8 at 12 / 11 / 10 bits) whose load, compute and store phases
+                             // interleave -- measured 88-97 % instead of 67-82 % of the HBM rate per pass --
+                             // but fewer qubits per pass; the planner takes the smallest tile a pass fits.
 #define QCS_LANE_BITS 5
 #define QCS_MAX_REG_BITS 4   // 16 amplitudes per thread (256-thread CTA) or 8 (512-thread CTA)
 #define QCS_MAX_PASS_GATES 240
@@ -113,6 +117,7 @@ struct DTileRun {
 struct PassParams {
   uint64_t shard_base;                 // rank << nl : high bits of every global index in this shard
   uint8_t tile_pos[QCS_TILE_BITS];     // physical position of each tile bit, ascending, [0..4] = 0..4
+  int32_t tile_bits;                   // T: tile_pos[0..T) are valid
   uint64_t nontile_mask;               // local positions that are not tile bits
   int32_t n_segments;
   int32_t n_gates;

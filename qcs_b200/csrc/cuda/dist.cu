@@ -138,7 +138,7 @@ p2p_swap_kernel(double2 *__restrict__ mine, double2 *__restrict__ peer, uint64_t
 int dist_open_peers(Engine &e) {
   DistContext &d = dist();
   if (!d.active || e.opt.dryrun) return QCS_CUDA_OK;
-  const size_t n_tiles = e.nl >= QCS_TILE_BITS ? (size_t)1 << (e.nl - QCS_TILE_BITS) : 0;
+  const size_t n_tiles = e.nl >= QCS_MIN_TILE_BITS ? (size_t)1 << (e.nl - QCS_MIN_TILE_BITS) : 0;
   if (n_tiles) {
     CK(cudaMalloc(&e.tile_flags, n_tiles * sizeof(uint32_t)));
     CK(cudaMemset(e.tile_flags, 0, n_tiles * sizeof(uint32_t)));

@@ -4,6 +4,7 @@
 // (SURVEY.md section 8b lists the sites) funnels through here.
 #include "engine.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -86,6 +87,9 @@ static int load_options(Options &o) {
   else return set_error(QCS_CUDA_ERR_INVALID, "exchange must be p2p|nccl, got '%s'", v.c_str());
   v = option_value("fuse_swaps");
   o.fuse_swaps = !(v == "off" || v == "0");
+  v = option_value("tile_bits");
+  if (!v.empty()) o.tile_bits = std::atoi(v.c_str());
+  if (o.tile_bits < QCS_MIN_TILE_BITS || o.tile_bits > QCS_TILE_BITS) o.tile_bits = Options().tile_bits;
   v = option_value("fixed_low");
   if (!v.empty()) o.fixed_low = std::atoi(v.c_str());
   if (o.fixed_low < 1 || o.fixed_low > QCS_LANE_BITS) o.fixed_low = Options().fixed_low;
@@ -251,6 +255,11 @@ static void trace_gates(Engine &e, const std::vector<PhysGate> &gates) {
   }
 }
 
+// smallest tile the selected kernel variant runs on (only ldg8 is instantiated below 12 bits)
+static int min_tile_bits(const Engine &e) {
+  return e.opt.tile_kernel == 3 ? std::min(QCS_MIN_TILE_BITS, e.opt.tile_bits) : QCS_TILE_BITS;
+}
+
 static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysGate> &gates) {
   PlannerConfig cfg;
   cfg.n_local = e.nl;
@@ -261,6 +270,8 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
   cfg.direct_io = true;
   cfg.reg_bits = (e.opt.tile_kernel >= 2) ? 3 : 4;
   cfg.fixed_low = e.opt.fixed_low;
+  cfg.tile_bits_min = min_tile_bits(e);
+  cfg.tile_bits_max = std::max(cfg.tile_bits_min, std::min(e.opt.tile_bits, e.nl));
   return plan_passes(gates, cfg);
 }
 
@@ -318,7 +329,7 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
 static int run_local(Engine &e, const std::vector<PhysGate> &gates) {
   if (gates.empty()) return QCS_CUDA_OK;
   if (e.opt.dryrun) trace_gates(e, gates);
-  const bool fused = e.opt.fusion && e.nl >= QCS_TILE_BITS;
+  const bool fused = e.opt.fusion && e.nl >= min_tile_bits(e);
   if (fused) {
     std::vector<PassPlan> plan = plan_batch(e, gates);
     RC(launch_passes(e, plan, 0, plan.size(), nullptr));
@@ -408,7 +419,7 @@ static int swap_positions(Engine &e, int lpos, int gpos) {
 // A swap can ride on the stores of a fused pass (SwapStore) when passes run through the plain-load
 // tile kernels and the partner's memory is mapped; plan-only engines follow the same schedule.
 static bool can_fuse_swaps(const Engine &e) {
-  if (!e.opt.fusion || e.nl < QCS_TILE_BITS || e.opt.sem != SEM_CORRECTED || e.opt.exchange != 1 ||
+  if (!e.opt.fusion || e.nl < min_tile_bits(e) || e.opt.sem != SEM_CORRECTED || e.opt.exchange != 1 ||
       !e.opt.fuse_swaps)
     return false;
   if (e.opt.tile_kernel != 0 && e.opt.tile_kernel != 3) return false;

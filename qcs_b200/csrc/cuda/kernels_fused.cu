@@ -206,31 +206,63 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 // Kernel bodies, instantiated for R = 4 (16 amplitudes/thread) and R = 3 (8).
 // ---------------------------------------------------------------------------
 #define QCS_R 4
-#define QCS_CT 256
+#define QCS_T 12
+#define QCS_CT (1 << (QCS_T - QCS_R))
+#define QCS_MIN_CTAS 2
 #define QCS_NREG_STR "16"
 #define QCS_LIST(x) QCS4_##x
 #define QCS_NAME(x) x##_r4
 #define QCS_WITH_LDG 1
+#define QCS_WITH_TMA 1
 #include "fused_body.inc"
 #undef QCS_R
+#undef QCS_T
 #undef QCS_CT
+#undef QCS_MIN_CTAS
 #undef QCS_NREG_STR
 #undef QCS_LIST
 #undef QCS_NAME
 #undef QCS_WITH_LDG
+#undef QCS_WITH_TMA
 
 #define QCS_R 3
-#define QCS_CT 512
 #define QCS_NREG_STR "8"
 #define QCS_LIST(x) QCS3_##x
-#define QCS_NAME(x) x##_r3
 #define QCS_WITH_LDG 1
+#define QCS_CT (1 << (QCS_T - QCS_R))
+
+#define QCS_T 12
+#define QCS_MIN_CTAS 2
+#define QCS_NAME(x) x##_r3
+#define QCS_WITH_TMA 1
 #include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+#undef QCS_WITH_TMA
+
+#define QCS_T 11
+#define QCS_MIN_CTAS 4
+#define QCS_NAME(x) x##_r3_t11
+#define QCS_WITH_TMA 0
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+
+#define QCS_T 10
+#define QCS_MIN_CTAS 8
+#define QCS_NAME(x) x##_r3_t10
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+#undef QCS_WITH_TMA
+
 #undef QCS_R
 #undef QCS_CT
 #undef QCS_NREG_STR
 #undef QCS_LIST
-#undef QCS_NAME
 #undef QCS_WITH_LDG
 
 // How many tiles ahead a CTA prefetches into L2 (QCS_CUDA_PREFETCH; off by default).
@@ -268,9 +300,12 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
   if (swap && variant != 0 && variant != 3) return cudaErrorInvalidValue;  // ldg kernels only
   SwapStore sw{};
   if (swap) sw = *swap;
-  const unsigned n_tiles = 1u << (n_local - QCS_TILE_BITS);
+  const int T = params.tile_bits;
+  if (T < QCS_MIN_TILE_BITS || T > QCS_TILE_BITS || T > n_local) return cudaErrorInvalidValue;
+  if (T != QCS_TILE_BITS && variant != 3) return cudaErrorInvalidValue;  // only ldg8 has small tiles
+  const unsigned n_tiles = 1u << (n_local - T);
   static int sm_count = 0;
-  static bool configured[4] = {false, false, false, false};
+  static bool configured[6] = {false, false, false, false, false, false};
   if (variant < 0 || variant > 3) return cudaErrorInvalidValue;
   if ((variant >= 2) != (params.reg_bits == 3)) return cudaErrorInvalidValue;
   if (sm_count == 0) {
@@ -282,8 +317,9 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
     sm_count = sms;
   }
   const size_t smem_tma = (size_t)kSlots * kTileBytes + 128;  // slots + barriers + tile origins
-  const size_t smem_ldg = (size_t)kTileBytes;
-  if (!configured[variant]) {
+  const size_t smem_ldg = (size_t)16 << T;
+  const int slot = variant == 3 ? 3 + (QCS_TILE_BITS - T) : variant;  // 3, 4, 5: ldg8 at 12, 11, 10 bits
+  if (!configured[slot]) {
     cudaError_t e;
     if (variant == 0)
       e = cudaFuncSetAttribute(fused_pass_ldg_r4, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -294,23 +330,34 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
     else if (variant == 2)
       e = cudaFuncSetAttribute(fused_pass_tma_r3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem_tma);
-    else
+    else if (T == 12)
       e = cudaFuncSetAttribute(fused_pass_ldg_r3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem_ldg);
+    else if (T == 11)
+      e = cudaFuncSetAttribute(fused_pass_ldg_r3_t11, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem_ldg);
+    else
+      e = cudaFuncSetAttribute(fused_pass_ldg_r3_t10, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem_ldg);
     if (e != cudaSuccess) return e;
-    configured[variant] = true;
+    configured[slot] = true;
   }
   const unsigned grid = n_tiles < (unsigned)sm_count ? n_tiles : (unsigned)sm_count;
+  const uint32_t pf = prefetch_distance(), st = stagger_ns();
   if (variant == 0) {
-    fused_pass_ldg_r4<<<n_tiles, 256, smem_ldg, stream>>>(state, params, prefetch_distance(), stagger_ns(), (uint32_t)sm_count, sw);
+    fused_pass_ldg_r4<<<n_tiles, 256, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
   } else if (variant == 1) {
     fused_pass_tma_r4<<<grid, 256 + 32, smem_tma, stream>>>(state, params, n_tiles,
                                                             (uint32_t)tile_row_bits(params));
   } else if (variant == 2) {
     fused_pass_tma_r3<<<grid, 512 + 32, smem_tma, stream>>>(state, params, n_tiles,
                                                             (uint32_t)tile_row_bits(params));
+  } else if (T == 12) {
+    fused_pass_ldg_r3<<<n_tiles, 512, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
+  } else if (T == 11) {
+    fused_pass_ldg_r3_t11<<<n_tiles, 256, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
   } else {
-    fused_pass_ldg_r3<<<n_tiles, 512, smem_ldg, stream>>>(state, params, prefetch_distance(), stagger_ns(), (uint32_t)sm_count, sw);
+    fused_pass_ldg_r3_t10<<<n_tiles, 128, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
   }
   return cudaGetLastError();
 }

@@ -82,12 +82,13 @@ static bool is_pairing(uint8_t kind) {
 // distinct residues mod 3 when possible so that, with the XOR swizzle used by the kernel
 // (slot ^ (slot>>3) ^ (slot>>6) ^ (slot>>9) on the low 3 bits), every quarter-warp of a 16-byte
 // shared-memory access hits 8 distinct bank groups.  Returns the lane cost of the choice.
-static double assign_roles(const std::vector<int> &regbits, const double lane_cost[QCS_TILE_BITS],
-                           bool force_low, uint8_t role_tilebit[QCS_TILE_BITS]) {
+static double assign_roles(int T, const std::vector<int> &regbits,
+                           const double lane_cost[QCS_TILE_BITS], bool force_low,
+                           uint8_t role_tilebit[QCS_TILE_BITS]) {
   bool is_reg[QCS_TILE_BITS] = {false};
   for (int b : regbits) is_reg[b] = true;
   std::vector<int> rest;
-  for (int b = 0; b < QCS_TILE_BITS; b++)
+  for (int b = 0; b < T; b++)
     if (!is_reg[b]) rest.push_back(b);
   const int n = (int)rest.size();
   auto residues_ok = [&](unsigned subset) {
@@ -122,7 +123,7 @@ static double assign_roles(const std::vector<int> &regbits, const double lane_co
       best_sum = sum;
     }
   }
-  if (!have) return assign_roles(regbits, lane_cost, false, role_tilebit);  // a register bit below 5
+  if (!have) return assign_roles(T, regbits, lane_cost, false, role_tilebit);  // a register bit below 5
   std::vector<int> lanes, warps;
   for (int i = 0; i < n; i++) (((best >> i) & 1u) ? lanes : warps).push_back(rest[i]);
   std::vector<int> lane_lo;
@@ -200,7 +201,13 @@ struct PassBuilder {
   bool fits(const PhysGate &g) const {
     if ((int)gates.size() + 1 > QCS_MAX_PASS_GATES) return false;
     if (!gates.empty() && flops + g.c.flops_per_amp > cfg.pass_flops_budget) return false;
-    if (is_pairing(g.c.kind) && !has(g.tpos) && (int)tile.size() >= QCS_TILE_BITS) return false;
+    if (is_pairing(g.c.kind) && !has(g.tpos)) {
+      if ((int)tile.size() >= cfg.tile_bits_max) return false;
+      // A pass that already carries enough arithmetic to be FP64-bound gains nothing from more
+      // qubits (its memory sweep is hidden anyway) and loses the finer CTA interleaving of a
+      // smaller tile: stop growing the tile, not the pass.
+      if ((int)tile.size() >= cfg.tile_bits_min && flops >= cfg.compute_bound_flops) return false;
+    }
     if (segments_needed(&g) > QCS_MAX_PASS_SEGMENTS) return false;
     return true;
   }
@@ -216,21 +223,24 @@ struct PassBuilder {
   PassPlan close() {
     PassPlan plan;
     std::memset(&plan.params, 0, sizeof(plan.params));
-    // Fill the tile with the lowest unused local positions (keeps rows long).
-    for (int p = cfg.fixed_low; (int)tile.size() < QCS_TILE_BITS && p < cfg.n_local; p++)
+    // The smallest tile that holds every pairing target; filled up with the lowest unused local
+    // positions (keeps rows long).
+    const int T = std::max(cfg.tile_bits_min, (int)tile.size());
+    for (int p = cfg.fixed_low; (int)tile.size() < T && p < cfg.n_local; p++)
       if (!has(p)) tile.push_back(p);
     std::sort(tile.begin(), tile.end());
     plan.tile_positions = tile;
     PassParams &pp = plan.params;
     pp.shard_base = cfg.shard_base;
+    pp.tile_bits = T;
     uint64_t tile_mask = 0;
-    for (int b = 0; b < QCS_TILE_BITS; b++) {
+    for (int b = 0; b < T; b++) {
       pp.tile_pos[b] = (uint8_t)tile[b];
       tile_mask |= 1ull << tile[b];
     }
     pp.nontile_mask = ((cfg.n_local >= 64 ? ~0ull : ((1ull << cfg.n_local) - 1))) & ~tile_mask;
     auto tilebit_of = [&](int pos) -> int {
-      for (int b = 0; b < QCS_TILE_BITS; b++)
+      for (int b = 0; b < T; b++)
         if (tile[b] == pos) return b;
       return -1;
     };
@@ -258,14 +268,14 @@ struct PassBuilder {
     // Complete register sets with spare tile bits (highest first, never below 5
     // unless forced) so that lanes keep the low bits.
     for (auto &s : segs) {
-      for (int b = QCS_TILE_BITS - 1; b >= 0 && (int)s.regbits.size() < cfg.reg_bits; b--)
+      for (int b = T - 1; b >= 0 && (int)s.regbits.size() < cfg.reg_bits; b--)
         if (std::find(s.regbits.begin(), s.regbits.end(), b) == s.regbits.end())
           s.regbits.push_back(b);
     }
     // Work a tile bit would waste as a lane bit of segment s: gates that test it once per thread
     // (a control or a diagonal target that is not a register bit) run with half the warp idle.
     auto lane_costs = [&](const Seg &s, double cost[QCS_TILE_BITS]) {
-      for (int b = 0; b < QCS_TILE_BITS; b++) cost[b] = 0.0;
+      for (int b = 0; b < T; b++) cost[b] = 0.0;
       auto is_reg = [&](int tb) {
         return std::find(s.regbits.begin(), s.regbits.end(), tb) != s.regbits.end();
       };
@@ -291,11 +301,11 @@ struct PassBuilder {
         double cost[QCS_TILE_BITS];
         uint8_t scratch[QCS_TILE_BITS];
         lane_costs(s, cost);
-        return assign_roles(s.regbits, cost, true, scratch) >
-               assign_roles(s.regbits, cost, false, scratch) + kSegmentCost;
+        return assign_roles(T, s.regbits, cost, true, scratch) >
+               assign_roles(T, s.regbits, cost, false, scratch) + kSegmentCost;
       };
       std::vector<int> io_regs;
-      for (int k = cfg.reg_bits; k >= 1; k--) io_regs.push_back(QCS_TILE_BITS - k);
+      for (int k = cfg.reg_bits; k >= 1; k--) io_regs.push_back(T - k);
       const bool front = wants_own_io(segs.front()), back = wants_own_io(segs.back());
       if (front) segs.insert(segs.begin(), Seg{io_regs, 0, 0});
       if (back) {
@@ -320,7 +330,7 @@ struct PassBuilder {
         double cost[QCS_TILE_BITS];
         lane_costs(segs[si], cost);
         const bool io = cfg.direct_io && (si == 0 || si == (int)segs.size() - 1);
-        assign_roles(segs[si].regbits, cost, io, ds.role_tilebit);
+        assign_roles(T, segs[si].regbits, cost, io, ds.role_tilebit);
       }
       ds.gate_begin = (uint16_t)out_n;
       auto reg_of = [&](int pos) -> int {
@@ -402,7 +412,7 @@ struct PassBuilder {
     plan.n_fan_headers = n_fans;
     // ---- tables that spare the kernel its per-tile index arithmetic ----------------------
     auto swz = [](uint32_t slot) { return slot ^ (((slot >> 3) ^ (slot >> 6) ^ (slot >> 9)) & 7u); };
-    const int thread_roles = QCS_TILE_BITS - cfg.reg_bits;
+    const int thread_roles = T - cfg.reg_bits;
     for (int si = 0; si < (int)segs.size(); si++) {
       DSegment &ds = pp.seg[si];
       for (int g = 0; g < 3; g++)
@@ -425,7 +435,7 @@ struct PassBuilder {
       for (int g = 0; g < 3; g++)
         for (int v = 0; v < 8; v++) {
           uint64_t off = 0;
-          for (int b = 0; b < QCS_TILE_BITS; b++)
+          for (int b = 0; b < T; b++)
             if ((ds.tb_lut[g][v] >> b) & 1) off |= 1ull << pp.tile_pos[b];
           ds.gb_lut[g][v] = off;
         }
@@ -487,7 +497,7 @@ std::string describe_plan(const std::vector<PassPlan> &passes) {
     std::snprintf(buf, sizeof(buf), "pass %zu: gates=%d api_gates=%d segments=%d flops/amp=%.1f tile=[",
                   pi, pp.n_gates, passes[pi].n_gates_api, pp.n_segments, passes[pi].flops_per_amp);
     s += buf;
-    for (int b = 0; b < QCS_TILE_BITS; b++) {
+    for (int b = 0; b < pp.tile_bits; b++) {
       std::snprintf(buf, sizeof(buf), "%s%d", b ? "," : "", pp.tile_pos[b]);
       s += buf;
     }
@@ -498,7 +508,7 @@ std::string describe_plan(const std::vector<PassPlan> &passes) {
       s += buf;
       for (int k = 0; k < pp.reg_bits; k++) {
         std::snprintf(buf, sizeof(buf), "%s%d", k ? "," : "",
-                      pp.tile_pos[ds.role_tilebit[QCS_TILE_BITS - pp.reg_bits + k]]);
+                      pp.tile_pos[ds.role_tilebit[pp.tile_bits - pp.reg_bits + k]]);
         s += buf;
       }
       std::snprintf(buf, sizeof(buf), "] gates %d..%d:", ds.gate_begin, ds.gate_end);

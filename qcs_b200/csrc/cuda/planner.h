@@ -50,6 +50,9 @@ struct PlannerConfig {
   double pass_flops_budget; // close a pass when its estimated flops/amp exceed this
   bool direct_io;           // true: first/last segment must keep tile bits 0..4 as lane bits
   int reg_bits;             // register-role bits per thread: 4 (16 amplitudes) or 3 (8)
+  int tile_bits_max = QCS_TILE_BITS;      // a pass may pair on at most this many positions ...
+  int tile_bits_min = QCS_TILE_BITS;      // ... and runs on the smallest tile >= this that holds them
+  double compute_bound_flops = 90.0;      // flops per amplitude above which a pass is FP64-bound
   int fixed_low = QCS_LANE_BITS;  // positions 0..fixed_low-1 belong to every tile: global rows of
                             // 16 << fixed_low contiguous bytes; the remaining tile bits are free
 };

@@ -80,16 +80,22 @@ def _random_script(rng, n, length, generic=True):
     return s
 
 
-@pytest.mark.parametrize("tile_kernel", ["tma", "tma16", "ldg", "ldg8"])
+# (tile kernel, largest tile): ldg8 runs on 10-, 11- or 12-bit tiles, the others on 12 only
+VARIANTS = [("tma", 12), ("tma16", 12), ("ldg", 12), ("ldg8", 12), ("ldg8", 11), ("ldg8", 10)]
+
+
+@pytest.mark.parametrize("tile_kernel,tile_bits", VARIANTS)
 @pytest.mark.parametrize("sem", ["reference", "corrected"])
-@pytest.mark.parametrize("n", [12, 13, 15, 17, 21])
-def test_fused_random_circuits_bit_exact(n, sem, tile_kernel):
-    """Fused tile passes (n >= 12) vs oracle: every amplitude equal, random start state."""
+@pytest.mark.parametrize("n", [10, 11, 12, 13, 15, 17, 21])
+def test_fused_random_circuits_bit_exact(n, sem, tile_kernel, tile_bits):
+    """Fused tile passes vs oracle: every amplitude equal, random start state."""
+    if n < (10 if tile_kernel == "ldg8" else 12):
+        pytest.skip("shard smaller than this variant's tile")
     rng = np.random.default_rng(1000 + n)
     for trial in range(4 if n < 20 else 1):
         script = _random_script(rng, n, 60 + 40 * trial)
         init = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
-        orc = po.Oracle(n, sem); c = Circuit(n, semantics=sem, tile_kernel=tile_kernel)
+        orc = po.Oracle(n, sem); c = Circuit(n, semantics=sem, tile_kernel=tile_kernel, tile_bits=tile_bits)
         orc.load_state(init); c.load_state(init)
         po.replay(orc, script); po.replay(c, script)
         got, want = c.state(), orc.state()
@@ -101,9 +107,9 @@ def test_fused_random_circuits_bit_exact(n, sem, tile_kernel):
         orc.close(); c.close()
 
 
-@pytest.mark.parametrize("tile_kernel", ["tma", "tma16", "ldg", "ldg8"])
+@pytest.mark.parametrize("tile_kernel,tile_bits", VARIANTS)
 @pytest.mark.parametrize("sem", ["reference", "corrected"])
-def test_every_target_control_pair(sem, tile_kernel):
+def test_every_target_control_pair(sem, tile_kernel, tile_bits):
     """Each (control, target) placement -- lane, warp, register, outside-tile bits -- for each gate class."""
     n = 14
     rng = np.random.default_rng(7)
@@ -117,7 +123,7 @@ def test_every_target_control_pair(sem, tile_kernel):
         "phase": [1, 0, 0, 0, 0, 0, 0.28, 0.96],
     }
     for cls, m in mats.items():
-        orc = po.Oracle(n, sem); c = Circuit(n, semantics=sem, tile_kernel=tile_kernel)
+        orc = po.Oracle(n, sem); c = Circuit(n, semantics=sem, tile_kernel=tile_kernel, tile_bits=tile_bits)
         orc.load_state(init); c.load_state(init)
         for t in range(n):
             orc.apply_1q(m, t); c.apply_1q(m, t)

@@ -42,17 +42,20 @@ def _parse(text):
 PAIRING = {"generic", "real", "hsym", "swap"}
 
 
-@pytest.mark.parametrize("tile_kernel,reg_bits", [("tma", 3), ("tma16", 4), ("ldg", 4), ("ldg8", 3)])
+@pytest.mark.parametrize("tile_kernel,reg_bits,tile_bits", [("tma", 3, 12), ("tma16", 4, 12), ("ldg", 4, 12),
+                                                            ("ldg8", 3, 12), ("ldg8", 3, 11), ("ldg8", 3, 10)])
 @pytest.mark.parametrize("n", [12, 20, 30, 34])
-def test_plan_invariants_random_circuit(n, tile_kernel, reg_bits):
+def test_plan_invariants_random_circuit(n, tile_kernel, reg_bits, tile_bits):
     script = po.random_circuit_script(n, 6)
-    text, st = _plan(n, script, semantics="corrected", tile_kernel=tile_kernel)
+    text, st = _plan(n, script, semantics="corrected", tile_kernel=tile_kernel, tile_bits=tile_bits)
     passes = _parse(text)
     assert passes and st["passes"] == len(passes)
     assert sum(p["api"] for p in passes) == len(script)
     for p in passes:
         tile = p["tile"]
-        assert len(tile) == 12 and tile == sorted(set(tile)) and tile[:5] == [0, 1, 2, 3, 4]
+        # a pass runs on the smallest tile (>= 10 bits for ldg8, else 12) that holds its pairing qubits
+        lo = 10 if tile_kernel == "ldg8" else 12
+        assert lo <= len(tile) <= max(lo, tile_bits) and tile == sorted(set(tile)) and tile[:5] == [0, 1, 2, 3, 4]
         assert all(t < n for t in tile)
         assert p["nseg"] == len(p["segs"]) <= 12
         # first and last segment keep the low five bits on the lanes (coalesced 512-byte rows)
