@@ -90,6 +90,9 @@ static int load_options(Options &o) {
   v = option_value("tile_bits");
   if (!v.empty()) o.tile_bits = std::atoi(v.c_str());
   if (o.tile_bits < QCS_MIN_TILE_BITS || o.tile_bits > QCS_TILE_BITS) o.tile_bits = Options().tile_bits;
+  v = option_value("compute_bound_flops");
+  if (!v.empty()) o.compute_bound_flops = std::atof(v.c_str());
+  if (!(o.compute_bound_flops > 0)) o.compute_bound_flops = Options().compute_bound_flops;
   v = option_value("fixed_low");
   if (!v.empty()) o.fixed_low = std::atoi(v.c_str());
   if (o.fixed_low < 1 || o.fixed_low > QCS_LANE_BITS) o.fixed_low = Options().fixed_low;
@@ -270,6 +273,7 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
   cfg.direct_io = true;
   cfg.reg_bits = (e.opt.tile_kernel >= 2) ? 3 : 4;
   cfg.fixed_low = e.opt.fixed_low;
+  cfg.compute_bound_flops = e.opt.compute_bound_flops;
   cfg.tile_bits_min = min_tile_bits(e);
   cfg.tile_bits_max = std::max(cfg.tile_bits_min, std::min(e.opt.tile_bits, e.nl));
   return plan_passes(gates, cfg);

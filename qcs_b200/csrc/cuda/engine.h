@@ -21,6 +21,7 @@ struct Options {
   int exchange = 0;  // 0: NCCL send/recv, 1: peer-memory swap kernel
   int tile_bits = 11;      // largest tile (10..12 bits) a pass may use; it runs on the smallest that fits.
                            // 11: measured best on the random circuits (12: 13 % fewer passes, each 25 % slower)
+  double compute_bound_flops = 90.0;  // a pass with this much FP64 work per amplitude stops growing its tile at 10 bits
   int fixed_low = 5;       // positions every tile contains (contiguous global rows of 16 << fixed_low bytes)
   int min_fused_victim = 5;  // lowest local position a pass-carried swap may trade away (2..5; measured: a
                              // qubit arriving at an always-in-tile position saves a pass in a QFT but its
