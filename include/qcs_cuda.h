@@ -155,6 +155,11 @@ long qcs_cuda_pass_descriptor_bytes(void);
  * (tile bits, segments, gates per segment) into buf; returns bytes needed. */
 long qcs_cuda_describe_last_plan(qcs_cuda_engine *e, char *buf, long cap);
 
+/* Copies the kernel-parameter block (PassParams, common.h) of pass `pass_index` of the last flush
+ * into buf (when cap is large enough); returns the number of passes of the last flush.  Lets a
+ * CPU test interpret exactly what the GPU would be handed (tests/test_planner.py). */
+long qcs_cuda_last_plan_raw(qcs_cuda_engine *e, long pass_index, void *buf, long cap);
+
 /* Dry-run engines record what a real engine would execute, in order.  Entry i is
  * written as 12 doubles: out[0] = 1 (gate) or 2 (position swap);
  *   gate: out[1] = kind | flags << 8 (common.h GateKind / GateFlags), out[2] = target position,

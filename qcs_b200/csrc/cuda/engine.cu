@@ -101,6 +101,14 @@ static int load_options(Options &o) {
   if (o.min_fused_victim < 0 || o.min_fused_victim > QCS_LANE_BITS) o.min_fused_victim = Options().min_fused_victim;
   v = option_value("peephole");
   o.peephole = !(v == "off" || v == "0");
+  v = option_value("math");
+  if (v == "fast") o.fast_math = true;
+  else if (v.empty() || v == "exact") o.fast_math = false;
+  else return set_error(QCS_CUDA_ERR_INVALID, "math must be exact|fast, got '%s'", v.c_str());
+  if (o.fast_math && (o.sem != SEM_CORRECTED || o.tile_kernel != 3))
+    return set_error(QCS_CUDA_ERR_INVALID,
+                     "math=fast needs semantics=corrected and tile_kernel=ldg8 (bug-compatible `reference` "
+                     "semantics are bit-exact by definition)");
   return QCS_CUDA_OK;
 }
 
@@ -274,6 +282,7 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
   cfg.reg_bits = (e.opt.tile_kernel >= 2) ? 3 : 4;
   cfg.fixed_low = e.opt.fixed_low;
   cfg.compute_bound_flops = e.opt.compute_bound_flops;
+  cfg.fast_math = e.opt.fast_math;
   cfg.tile_bits_min = min_tile_bits(e);
   cfg.tile_bits_max = std::max(cfg.tile_bits_min, std::min(e.opt.tile_bits, e.nl));
   return plan_passes(gates, cfg);
@@ -305,10 +314,10 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
         sw.lpos_in_tile = 0;
         for (int pos : p.tile_positions)
           if ((uint32_t)pos == sw.lpos) sw.lpos_in_tile = 1;
-        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, &sw));
+        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, &sw, e.opt.fast_math));
         RC(dist_after_fused_swap(e));
       } else {
-        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel));
+        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, nullptr, e.opt.fast_math));
       }
     }
     e.passes++;
@@ -1243,6 +1252,13 @@ long qcs_cuda_describe_last_plan(qcs_cuda_engine *e, char *buf, long cap) {
     buf[n] = 0;
   }
   return (long)s.size() + 1;
+}
+
+long qcs_cuda_last_plan_raw(qcs_cuda_engine *e, long pass_index, void *buf, long cap) {
+  if (!e) return 0;
+  if (buf && pass_index >= 0 && pass_index < (long)e->last_plan.size() && cap >= (long)sizeof(PassParams))
+    std::memcpy(buf, &e->last_plan[(size_t)pass_index].params, sizeof(PassParams));
+  return (long)e->last_plan.size();
 }
 
 }  // extern "C"

@@ -26,6 +26,10 @@ struct Options {
   int min_fused_victim = 5;  // lowest local position a pass-carried swap may trade away (2..5; measured: a
                              // qubit arriving at an always-in-tile position saves a pass in a QFT but its
                              // 64..256-byte remote store runs cost 1.5-3 ms per swap: no net gain)
+  bool fast_math = false;  // math=fast (opt-in, corrected semantics, ldg8 kernels): fused multiply-adds and
+                           // controlled-phase fans collapsed into one factor per thread.  Amplitudes then
+                           // agree with the reference to ~1e-15 relative (tested at 1e-12, the north star's
+                           // bar) instead of bit for bit; the default (math=exact) stays bit-exact.
   bool peephole = true;    // drop exactly self-cancelling gate pairs from the queue (corrected semantics)
   bool fuse_swaps = true;  // fold position swaps into the stores of a pass (peer-memory path only)
   int tile_kernel = 3;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8), 3: ldg8 (512 thr x 8 amps, plain loads; default)

@@ -72,6 +72,62 @@ def cmul(xr, xi, gr, gi, v):
             f"mul.rn.f64 {xi}, {gr}, qi{v};", f"mul.rn.f64 u0, {gi}, qr{v};", f"add.rn.f64 {xi}, {xi}, u0;"]
 
 
+def cmul_fast(xr, xi, gr, gi, ngi, v, acc):
+    """fast mode: x (+)= g * v with fused multiply-adds; ngi = register holding -g.i.
+    acc=False starts the chain with a plain product."""
+    if acc:
+        return [f"fma.rn.f64 {xr}, {gr}, qr{v}, {xr};", f"fma.rn.f64 {xr}, {ngi}, qi{v}, {xr};",
+                f"fma.rn.f64 {xi}, {gr}, qi{v}, {xi};", f"fma.rn.f64 {xi}, {gi}, qr{v}, {xi};"]
+    return [f"mul.rn.f64 {xr}, {gr}, qr{v};", f"fma.rn.f64 {xr}, {ngi}, qi{v}, {xr};",
+            f"mul.rn.f64 {xi}, {gr}, qi{v};", f"fma.rn.f64 {xi}, {gi}, qr{v}, {xi};"]
+
+
+def op_pair_fast(kind, row0, a, b):
+    """math=fast: the same update with fused multiply-adds (results within a few ulp of the
+    reference's separately rounded ones; never used in the bit-exact mode).  n* registers hold
+    negated matrix entries (pair_loads_fast)."""
+    if kind == "HSYM":
+        o = [f"mul.rn.f64 t0, g0, qr{a};", f"mul.rn.f64 t1, g0, qi{a};",
+             f"fma.rn.f64 qr{a}, g2, qr{b}, t0;", f"fma.rn.f64 qi{a}, g2, qi{b}, t1;"]
+        if not row0:
+            o += [f"fma.rn.f64 qr{b}, n2, qr{b}, t0;", f"fma.rn.f64 qi{b}, n2, qi{b}, t1;"]
+        return o
+    if kind == "REAL":
+        o = [f"mul.rn.f64 t0, g0, qr{a};", f"mul.rn.f64 t1, g0, qi{a};"]
+        if not row0:
+            o += [f"mul.rn.f64 t4, g4, qr{a};", f"mul.rn.f64 t5, g4, qi{a};"]
+        o += [f"fma.rn.f64 qr{a}, g2, qr{b}, t0;", f"fma.rn.f64 qi{a}, g2, qi{b}, t1;"]
+        if not row0:
+            o += [f"fma.rn.f64 qr{b}, g6, qr{b}, t4;", f"fma.rn.f64 qi{b}, g6, qi{b}, t5;"]
+        return o
+    if kind == "SWAP":
+        return op_pair(kind, row0, a, b)
+    o = cmul_fast("t0", "t1", "g0", "g1", "n1", a, False) + cmul_fast("t0", "t1", "g2", "g3", "n3", b, True)
+    if not row0:
+        o += cmul_fast("t4", "t5", "g4", "g5", "n5", a, False) + cmul_fast("t4", "t5", "g6", "g7", "n7", b, True)
+    o += [f"mov.f64 qr{a}, t0;", f"mov.f64 qi{a}, t1;"]
+    if not row0:
+        o += [f"mov.f64 qr{b}, t4;", f"mov.f64 qi{b}, t5;"]
+    return o
+
+
+def pair_loads_fast(kind, row0):
+    o = pair_loads(kind, row0)
+    if kind == "HSYM" and not row0:
+        o += ["neg.f64 n2, g2;"]
+    if kind == "GENERIC":
+        o += ["neg.f64 n1, g1;", "neg.f64 n3, g3;"]
+        if not row0:
+            o += ["neg.f64 n5, g5;", "neg.f64 n7, g7;"]
+    return o
+
+
+def op_diag_fast(r, er="dr", ei="di"):
+    """math=fast: amplitude r *= (er, ei) with fused multiply-adds"""
+    return [f"mul.rn.f64 t0, {ei}, qi{r};", f"mul.rn.f64 t1, {ei}, qr{r};", "neg.f64 t0, t0;",
+            f"fma.rn.f64 qr{r}, {er}, qr{r}, t0;", f"fma.rn.f64 qi{r}, {er}, qi{r}, t1;"]
+
+
 def op_pair(kind, row0, a, b):
     """a = register with target bit 0, b = target bit 1.  Operation order = c_add(c_mul(g0,v0),
     c_mul(g1,v1)) (reference src/q_gates.c:140-141); row0 = reference-semantics controlled update."""
@@ -130,8 +186,15 @@ def thread_bit_test(field_shift, pred="p"):
             f"setp.ne.u64 {pred}, t64, 0;"]
 
 
-def emit(R):
-    P = f"QCS{R}"
+def emit(R, fast=False):
+    """fast=False: the bit-exact interpreter.  fast=True (math=fast, R = 3 only): the same case
+    labels and record layout, fused multiply-adds, and controlled-phase fans that multiply the
+    entries' phases into ONE per-thread factor (looked up four entries at a time in tables the
+    planner lays over the entries' matrix slots) before touching the amplitudes."""
+    P = f"QCS{R}F" if fast else f"QCS{R}"
+    pair_body = op_pair_fast if fast else op_pair
+    pair_ld = pair_loads_fast if fast else pair_loads
+    diag_body = op_diag_fast if fast else op_diag
     labels = {}          # symbolic id -> case label (consecutive)
     blocks = []          # (label name, [ptx lines])
 
@@ -154,9 +217,9 @@ def emit(R):
                     if c == t:
                         continue
                     sym = ((ki * 2 + row0) * 4 + t) * 5 + (c + 1)
-                    body = pair_loads(kind, row0)
+                    body = pair_ld(kind, row0)
                     for a, b in pairs(R, t, c):
-                        body += op_pair(kind, row0, a, b)
+                        body += pair_body(kind, row0, a, b)
                     case(sym, body, c < 0)
     # diagonal, target NOT a register bit: id = 160 + (creg+1)*3 + (halves-1); the thread's own target
     # bit picks the entry.  halves: 1 = only entry 0 is not the identity, 2 = only entry 1, 3 = both
@@ -171,7 +234,7 @@ def emit(R):
             else:
                 body += ["@p bra DONE;", f"ld.param.f64 dr, [%1+{OFF_M(0)}];", f"ld.param.f64 di, [%1+{OFF_M(1)}];"]
             for r in regs(R, c=c):
-                body += op_diag(r)
+                body += diag_body(r)
             case(sym, body, c < 0)
     # diagonal, target = register bit t: id = 175 + (t*5 + creg+1)*3 + (halves-1)
     for t in range(R):
@@ -184,11 +247,11 @@ def emit(R):
                 if halves & 1:
                     body += ld_m([0, 1])
                     for r in regs(R, t, 0, c):
-                        body += op_diag(r, "g0", "g1")
+                        body += diag_body(r, "g0", "g1")
                 if halves & 2:
                     body += ld_m([6, 7])
                     for r in regs(R, t, 1, c):
-                        body += op_diag(r, "g6", "g7")
+                        body += diag_body(r, "g6", "g7")
                 case(sym, body, c < 0)
     # controlled-phase fan (id 240 + treg + 1; header layout: common.h QCS_OP_FAN_BASE): K consecutive
     # gates diag(1, e^{i a_k}) on ONE target, each controlled by a bit that is not a register bit.
@@ -208,6 +271,35 @@ def emit(R):
             body += [f"ld.param.u8 cs, [%1+{OFF_TPOS}];", "shr.u64 t64, %2, cs;", "and.b64 t64, t64, 1;",
                      "setp.eq.u64 p, t64, 0;", "@p mov.u32 mask, 0;"]
         diag_regs = regs(R, t, 1) if t >= 0 else regs(R)
+        if fast:
+            # Table walk (planner.cpp write_fan_tables): group i = entries 4i..4i+3; its 16 products
+            # sit in the m[] slots of those four records, product j at record 4i + (j >> 2), slot
+            # j & 3.  One lookup + one complex multiply-add per group, whatever the entry count;
+            # groups in which no lane of the warp takes part are skipped.
+            body += ["mov.b32 tst, mask;",  # this thread's own mask, kept for the final test
+                     "mov.f64 ar, 0d3FF0000000000000;", "mov.f64 ai, 0d0000000000000000;",
+                     "redux.sync.or.b32 wm, mask, 0xffffffff;", f"add.u64 ea, %1, {E};",
+                     f"FL{n}:", "setp.eq.u32 p, wm, 0;", f"@p bra FE{n};",
+                     "and.b32 low, wm, 15;", "setp.eq.u32 pa, low, 0;", f"@pa bra FS{n};",
+                     "and.b32 low, mask, 15;", "shr.u32 kidx, low, 2;", "and.b32 low, low, 3;",
+                     f"mul.lo.u32 kidx, kidx, {E};", "mad.lo.u32 kidx, low, 16, kidx;",
+                     "cvt.u64.u32 t64, kidx;", "add.u64 t64, t64, ea;",
+                     "ld.param.v2.f64 {dr, di}, [t64];",
+                     "mul.rn.f64 t0, ai, di;", "mul.rn.f64 t1, ai, dr;", "neg.f64 t0, t0;",
+                     "fma.rn.f64 t2, ar, dr, t0;", "fma.rn.f64 ai, ar, di, t1;", "mov.f64 ar, t2;",
+                     f"FS{n}:", "shr.u32 mask, mask, 4;", "shr.u32 wm, wm, 4;",
+                     f"add.u64 ea, ea, {4 * E};", f"bra FL{n};",
+                     f"FE{n}:", "setp.eq.u32 p, tst, 0;", f"@p bra FX{n};"]
+            for r in diag_regs:
+                body += op_diag_fast(r, "ar", "ai")
+            body += [f"FX{n}:", "add.s32 %0, %0, K;", "bra DONE;",
+                     f"FG{n}:", "mov.u32 mask, 0;", "mov.u32 kidx, 0;", "mov.u64 ea, %1;",
+                     f"FH{n}:", f"ld.param.u8 cs, [ea+{E + OFF_CPOS}];", "shr.u64 t64, %2, cs;",
+                     "cvt.u32.u64 tst, t64;", "and.b32 tst, tst, 1;", "shl.b32 tst, tst, kidx;",
+                     "or.b32 mask, mask, tst;", f"add.u64 ea, ea, {E};", "add.u32 kidx, kidx, 1;",
+                     "setp.lt.u32 p, kidx, K;", f"@p bra FH{n};", f"bra FM{n};"]
+            blocks.append((new_case(sym), body))
+            continue
         entry = ["bfind.u32 kidx, low;", f"mul.wide.u32 ea, kidx, {E};", "add.u64 ea, ea, %1;",
                  f"ld.param.v2.f64 {{dr, di}}, [ea+{E + OFF_M(6)}];"]
         for r in diag_regs:
@@ -237,7 +329,7 @@ def emit(R):
 
     n_cases = len(labels)
     text = ["{", ".reg .b32 w0, op, cs, c0, K, mask, wm, low, tst, kidx;", ".reg .b64 t64, ea;",
-            ".reg .pred p, pa;", ".reg .f64 g<8>, t<8>, u0, dr, di;",
+            ".reg .pred p, pa;", ".reg .f64 g<8>, t<8>, n<8>, u0, dr, di, ar, ai;",
             f"ld.param.u32 w0, [%1+{OFF_W0}];", "add.s32 %0, %0, 1;", "and.b32 op, w0, 0xffff;",
             "TS: .branchtargets " + ", ".join(f"C{i}" for i in range(n_cases)) + ";",
             "brx.idx op, TS;"]
@@ -264,10 +356,13 @@ def main():
         for R in (3, 4):
             out += emit(R)[0]
             out.append("")
+        out += emit(3, fast=True)[0]
+        out.append("")
     else:
         out = ["// GENERATED by gen_fused_lists.py -- do not edit.",
                "// symbolic op id (common.h qcs_op_id_*, | QCS_OP_TCTL) -> case label of the generated jump table",
                "#pragma once", ""]
+        assert emit(3, fast=True)[1] == emit(3)[1]  # one label table serves both interpreters
         for R in (3, 4):
             table = emit(R)[1]
             out.append(f"static const unsigned short QCS{R}_CASE_LABEL[512] = {{")

@@ -22,8 +22,11 @@ struct SwapStore {
   uint32_t my_gbit;           // my value of that rank bit
   uint32_t lpos_in_tile;      // lpos is one of the pass's tile positions
 };
+// fast (ldg8 only): the fused-multiply-add interpreter; `params` must come from a planner run with
+// PlannerConfig::fast_math (fan entries carry product tables instead of single phases).
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
-                              cudaStream_t stream, int variant, const SwapStore *swap = nullptr);
+                              cudaStream_t stream, int variant, const SwapStore *swap = nullptr,
+                              bool fast = false);
 
 // kernels_simple.cu: one launch per gate (fusion off, shards below one tile) ---
 cudaError_t launch_simple_gate(double2 *state, const DGate &g, int n_local,

@@ -259,6 +259,36 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 #undef QCS_NAME
 #undef QCS_WITH_TMA
 
+// math=fast: the same three ldg8 kernels around the fused-multiply-add interpreter (QCS3F_*)
+#undef QCS_LIST
+#define QCS_LIST(x) QCS3F_##x
+#define QCS_WITH_TMA 0
+
+#define QCS_T 12
+#define QCS_MIN_CTAS 2
+#define QCS_NAME(x) x##_r3f
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+
+#define QCS_T 11
+#define QCS_MIN_CTAS 4
+#define QCS_NAME(x) x##_r3f_t11
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+
+#define QCS_T 10
+#define QCS_MIN_CTAS 8
+#define QCS_NAME(x) x##_r3f_t10
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+#undef QCS_WITH_TMA
+
 #undef QCS_R
 #undef QCS_CT
 #undef QCS_NREG_STR
@@ -296,8 +326,9 @@ static int tile_row_bits(const PassParams &p) {
 }  // namespace
 
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
-                              cudaStream_t stream, int variant, const SwapStore *swap) {
+                              cudaStream_t stream, int variant, const SwapStore *swap, bool fast) {
   if (swap && variant != 0 && variant != 3) return cudaErrorInvalidValue;  // ldg kernels only
+  if (fast && variant != 3) return cudaErrorInvalidValue;  // math=fast exists for ldg8 only
   SwapStore sw{};
   if (swap) sw = *swap;
   const int T = params.tile_bits;
@@ -305,7 +336,7 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
   if (T != QCS_TILE_BITS && variant != 3) return cudaErrorInvalidValue;  // only ldg8 has small tiles
   const unsigned n_tiles = 1u << (n_local - T);
   static int sm_count = 0;
-  static bool configured[6] = {false, false, false, false, false, false};
+  static bool configured[9] = {false, false, false, false, false, false, false, false, false};
   if (variant < 0 || variant > 3) return cudaErrorInvalidValue;
   if ((variant >= 2) != (params.reg_bits == 3)) return cudaErrorInvalidValue;
   if (sm_count == 0) {
@@ -318,10 +349,14 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
   }
   const size_t smem_tma = (size_t)kSlots * kTileBytes + 128;  // slots + barriers + tile origins
   const size_t smem_ldg = (size_t)16 << T;
-  const int slot = variant == 3 ? 3 + (QCS_TILE_BITS - T) : variant;  // 3, 4, 5: ldg8 at 12, 11, 10 bits
+  // 3, 4, 5: ldg8 at 12, 11, 10 bits; 6, 7, 8: the same with math=fast
+  const int slot = variant == 3 ? 3 + (QCS_TILE_BITS - T) + (fast ? 3 : 0) : variant;
   if (!configured[slot]) {
     cudaError_t e;
-    if (variant == 0)
+    if (fast)
+      e = cudaFuncSetAttribute(T == 12 ? fused_pass_ldg_r3f : T == 11 ? fused_pass_ldg_r3f_t11 : fused_pass_ldg_r3f_t10,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ldg);
+    else if (variant == 0)
       e = cudaFuncSetAttribute(fused_pass_ldg_r4, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem_ldg);
     else if (variant == 1)
@@ -344,7 +379,14 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
   }
   const unsigned grid = n_tiles < (unsigned)sm_count ? n_tiles : (unsigned)sm_count;
   const uint32_t pf = prefetch_distance(), st = stagger_ns();
-  if (variant == 0) {
+  if (fast) {
+    if (T == 12)
+      fused_pass_ldg_r3f<<<n_tiles, 512, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
+    else if (T == 11)
+      fused_pass_ldg_r3f_t11<<<n_tiles, 256, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
+    else
+      fused_pass_ldg_r3f_t10<<<n_tiles, 128, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
+  } else if (variant == 0) {
     fused_pass_ldg_r4<<<n_tiles, 256, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
   } else if (variant == 1) {
     fused_pass_tma_r4<<<grid, 256 + 32, smem_tma, stream>>>(state, params, n_tiles,

@@ -148,6 +148,57 @@ static double assign_roles(int T, const std::vector<int> &regbits,
   return best_cost;
 }
 
+// math=fast cost of a gate in FP64 instructions per amplitude (fused multiply-adds; a controlled
+// phase is one table lookup shared by four fan entries plus its share of one complex multiply).
+static double fast_flops(const PhysGate &g) {
+  const double ctrl_frac = g.cpos >= 0 ? 0.5 : 1.0;
+  const double row = (g.c.flags & GF_ROW0_ONLY) ? 0.5 : 1.0;
+  switch (g.c.kind) {
+    case GK_PAIR_HSYM: return 3.0 * ctrl_frac * row;
+    case GK_PAIR_REAL: return 4.0 * ctrl_frac * row;
+    case GK_PAIR_GENERIC: return 8.0 * ctrl_frac * row;
+    case GK_DIAG: {
+      const int touched = ((g.c.flags & GF_D0_IDENT) ? 0 : 1) + ((g.c.flags & GF_D1_IDENT) ? 0 : 1);
+      if (g.cpos >= 0 && touched == 1) return 0.5;
+      return 4.0 * 0.5 * touched * ctrl_frac;
+    }
+    default: return g.c.flops_per_amp;
+  }
+}
+
+// math=fast layout of a controlled-phase fan (header at record h, K entries behind it): the kernel
+// multiplies the phases of the entries a thread takes part in into ONE factor before it touches an
+// amplitude, four entries per step.  Group i = entries 4i..4i+3; the 16 products over the subsets of
+// the group (product j = phases of the entries whose bit is set in j; product 0 = 1) replace the
+// matrix slots of the group's records: product j sits in record 4i + (j >> 2), m[2 (j & 3)..+1].
+// A last group of r < 4 entries needs 2^r <= 4 r slots, so everything fits in place.  Products are
+// formed in long double and rounded once.
+static void write_fan_tables(PassParams &pp, int h) {
+  const int K = pp.gate[h].tsel;
+  long double ph[QCS_MAX_FAN_ENTRIES][2];
+  for (int k = 0; k < K; k++) {
+    ph[k][0] = pp.gate[h + 1 + k].m[6];
+    ph[k][1] = pp.gate[h + 1 + k].m[7];
+  }
+  for (int k = 0; k < K; k++) std::memset(pp.gate[h + 1 + k].m, 0, sizeof(pp.gate[0].m));
+  for (int i = 0; 4 * i < K; i++) {
+    const int r = std::min(4, K - 4 * i);
+    for (int j = 0; j < (1 << r); j++) {
+      long double re = 1.0L, im = 0.0L;
+      for (int b = 0; b < r; b++)
+        if ((j >> b) & 1) {
+          const long double nre = re * ph[4 * i + b][0] - im * ph[4 * i + b][1];
+          const long double nim = re * ph[4 * i + b][1] + im * ph[4 * i + b][0];
+          re = nre;
+          im = nim;
+        }
+      DGate &rec = pp.gate[h + 1 + 4 * i + (j >> 2)];
+      rec.m[2 * (j & 3)] = (double)re;
+      rec.m[2 * (j & 3) + 1] = (double)im;
+    }
+  }
+}
+
 namespace {
 
 struct PassBuilder {
@@ -410,6 +461,9 @@ struct PassBuilder {
     }
     pp.n_gates = out_n;
     plan.n_fan_headers = n_fans;
+    if (cfg.fast_math)
+      for (int h = 0; h < out_n; h++)
+        if (pp.gate[h].flags & GF_FAN_HEADER) write_fan_tables(pp, h);
     // ---- tables that spare the kernel its per-tile index arithmetic ----------------------
     auto swz = [](uint32_t slot) { return slot ^ (((slot >> 3) ^ (slot >> 6) ^ (slot >> 9)) & 7u); };
     const int thread_roles = T - cfg.reg_bits;
@@ -468,8 +522,11 @@ struct PassBuilder {
 
 }  // namespace
 
-std::vector<PassPlan> plan_passes(const std::vector<PhysGate> &gates, const PlannerConfig &cfg) {
+std::vector<PassPlan> plan_passes(const std::vector<PhysGate> &gates_in, const PlannerConfig &cfg) {
   std::vector<PassPlan> out;
+  std::vector<PhysGate> gates = gates_in;
+  if (cfg.fast_math)
+    for (PhysGate &g : gates) g.c.flops_per_amp = fast_flops(g);
   PassBuilder *b = new PassBuilder(cfg);
   for (const PhysGate &g : gates) {
     if (g.c.kind != GK_NOP && !b->fits(g)) {

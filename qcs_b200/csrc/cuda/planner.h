@@ -53,6 +53,8 @@ struct PlannerConfig {
   int tile_bits_max = QCS_TILE_BITS;      // a pass may pair on at most this many positions ...
   int tile_bits_min = QCS_TILE_BITS;      // ... and runs on the smallest tile >= this that holds them
   double compute_bound_flops = 90.0;      // flops per amplitude above which a pass is FP64-bound
+  bool fast_math = false;   // math=fast: plan for the fused-multiply-add interpreter -- cost estimates count
+                            // FMA instructions, fan entries carry product tables (write_fan_tables)
   int fixed_low = QCS_LANE_BITS;  // positions 0..fixed_low-1 belong to every tile: global rows of
                             // 16 << fixed_low contiguous bytes; the remaining tile bits are free
 };

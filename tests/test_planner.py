@@ -128,3 +128,81 @@ def test_queue_peephole_drops_only_exact_pairs():
     # reference semantics: never (a controlled X is not an involution there, the scratch buffer is observable)
     _, st = _plan(14, [("x", 3), ("x", 3)], semantics="reference")
     assert st["gates_executed"] == 2 and st["gates_cancelled"] == 0
+
+
+# ---- the descriptors themselves, interpreted on the CPU (tests/plan_emulator.py) -------------
+def _close(got, want, tol=1e-12):
+    """SURVEY 8(c) metric: |delta| <= tol * max|want| everywhere, relative where amplitudes are not tiny."""
+    scale = np.abs(want).max()
+    err = np.abs(got - want)
+    assert err.max() <= tol * scale, err.max() / scale
+    big = np.abs(want) >= 1e-3 * scale
+    assert (err[big] / np.abs(want[big])).max() <= tol
+
+
+def _fan_script(n, seed):
+    """Runs of controlled phases on one target with consecutive and scattered controls, H's in between
+    (fans of every length 1..n-1, both mask paths of the kernel)."""
+    rng = np.random.default_rng(seed)
+    script = [("h", q) for q in range(n)]
+    for t in range(n):
+        ctrls = [q for q in range(n) if q != t]
+        if t % 2:
+            rng.shuffle(ctrls)
+        ctrls = ctrls[: 1 + int(rng.integers(0, n - 1))]
+        script += [("cphase", c, t, float(rng.uniform(-3, 3))) for c in ctrls]
+        script += [("h", int(rng.integers(0, n))), ("rz", int(rng.integers(0, n)), float(rng.uniform(-3, 3)))]
+    return script
+
+
+@pytest.mark.parametrize("math", ["exact", "fast"])
+@pytest.mark.parametrize("tile_bits", [10, 11, 12])
+@pytest.mark.parametrize("case", ["qft", "random+qft", "fans", "generic"])
+def test_descriptors_compute_the_circuit(case, tile_bits, math):
+    from qcs_b200 import Circuit
+    from tests import plan_emulator as pe
+    n = 13
+    if case == "qft":
+        # a dense start state: on a basis state the QFT's controls are all |0> and its fans do nothing
+        script = [("h", q) for q in range(n)] + [("ry", q, 0.3 + 0.1 * q) for q in range(n)] + [("qft",)]
+    elif case == "random+qft":
+        script = po.random_circuit_script(n, 5, seed=99) + [("qft",)]
+    elif case == "fans":
+        script = _fan_script(n, 5)
+    else:
+        rng = np.random.default_rng(3)
+        script = []
+        for _ in range(60):
+            q = int(rng.integers(0, n))
+            script.append([("rx", q, float(rng.uniform(-3, 3))), ("ry", q, float(rng.uniform(-3, 3))),
+                           ("y", q), ("phase", q, float(rng.uniform(-3, 3))), ("z", q),
+                           ("cnot", q, (q + 1 + int(rng.integers(0, n - 1))) % n)][int(rng.integers(0, 6))])
+    orc = po.Oracle(n, "corrected")
+    po.replay(orc, script)
+    want = orc.state()
+    orc.close()
+    c = Circuit(n, dryrun=True, semantics="corrected", tile_kernel="ldg8", tile_bits=tile_bits, math=math,
+                peephole="off")
+    po.replay(c, script)
+    c.flush()
+    passes = pe.read_plan(c)
+    assert len(passes) == c.stats()["passes"] > 0
+    got = pe.run_plan(passes, n, fast=(math == "fast"))
+    c.close()
+    _close(got, want)
+    if math == "fast" and case != "generic":
+        # the check has teeth: reading the product tables as plain phases gives a different state
+        n_fans = sum(1 for p in passes for g in list(p.gate)[: p.n_gates] if g.flags & pe.GF_FAN_HEADER)
+        assert n_fans > 0
+        wrong = pe.run_plan(passes, n, fast=False)
+        assert np.abs(wrong - want).max() > 1e-6
+
+
+def test_fast_math_needs_corrected_semantics_and_ldg8():
+    from qcs_b200 import Circuit
+    from qcs_b200.circuit import QcsError
+    for kw in ({"semantics": "reference"}, {"semantics": "corrected", "tile_kernel": "tma"}):
+        with pytest.raises(QcsError):
+            Circuit(12, dryrun=True, math="fast", **kw)
+    with pytest.raises(QcsError):
+        Circuit(12, dryrun=True, semantics="corrected", math="sloppy")
