@@ -105,6 +105,11 @@ static int load_options(Options &o) {
   if (v == "fast") o.fast_math = true;
   else if (v.empty() || v == "exact") o.fast_math = false;
   else return set_error(QCS_CUDA_ERR_INVALID, "math must be exact|fast, got '%s'", v.c_str());
+  v = option_value("reorder");
+  o.reorder = !(v == "off" || v == "0");
+  v = option_value("reorder_segments");
+  if (!v.empty()) o.reorder_segments = std::atoi(v.c_str());
+  if (o.reorder_segments < 1 || o.reorder_segments > QCS_MAX_PASS_SEGMENTS) o.reorder_segments = Options().reorder_segments;
   if (o.fast_math && (o.sem != SEM_CORRECTED || o.tile_kernel != 3))
     return set_error(QCS_CUDA_ERR_INVALID,
                      "math=fast needs semantics=corrected and tile_kernel=ldg8 (bug-compatible `reference` "
@@ -283,6 +288,10 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
   cfg.fixed_low = e.opt.fixed_low;
   cfg.compute_bound_flops = e.opt.compute_bound_flops;
   cfg.fast_math = e.opt.fast_math;
+  // sharded engines cut the queue at position swaps and hoist those onto passes by queue index
+  // (run_range): their passes stay in queue order
+  cfg.reorder = e.opt.fast_math && e.opt.reorder && !dist().active;
+  cfg.reorder_segments = e.opt.reorder_segments;
   cfg.tile_bits_min = min_tile_bits(e);
   cfg.tile_bits_max = std::max(cfg.tile_bits_min, std::min(e.opt.tile_bits, e.nl));
   return plan_passes(gates, cfg);

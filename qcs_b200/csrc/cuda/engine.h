@@ -30,6 +30,9 @@ struct Options {
                            // controlled-phase fans collapsed into one factor per thread.  Amplitudes then
                            // agree with the reference to ~1e-15 relative (tested at 1e-12, the north star's
                            // bar) instead of bit for bit; the default (math=exact) stays bit-exact.
+  bool reorder = true;     // math=fast, single GPU: commuting gates may trade places so that a pass follows its
+                           // tile through several circuit layers (planner.h PlannerConfig::reorder)
+  int reorder_segments = 8;
   bool peephole = true;    // drop exactly self-cancelling gate pairs from the queue (corrected semantics)
   bool fuse_swaps = true;  // fold position swaps into the stores of a pass (peer-memory path only)
   int tile_kernel = 3;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8), 3: ldg8 (512 thr x 8 amps, plain loads; default)

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 
 namespace qcs {
 
@@ -522,11 +523,152 @@ struct PassBuilder {
 
 }  // namespace
 
+// ---- math=fast: commutation-aware scheduling ------------------------------------------------------
+// Two gates commute when every qubit they share is a control or a diagonal target of BOTH (both are
+// then block-diagonal in those qubits and act on disjoint qubits inside each block).  In floating
+// point the two orders round differently, so the bit-exact mode never uses this; math=fast does.
+// A pass becomes a subsequence of the queue: what can run with pairing targets inside one tile,
+// segment after segment, following the circuit several layers deep where the in-order cut would
+// stop at the first qubit outside the tile (a brickwork layer touches every qubit).
+namespace {
+
+// One in-order sweep over the pending gates: which of them can run now if only positions in `rmask`
+// may be paired?  A gate that cannot run leaves its qubits pending: a pending pairing use blocks
+// every later use of that position, a pending diagonal-like use blocks later pairing uses only.
+struct Sweep {
+  std::vector<int> picked;  // indices into the gate list, ascending
+  int pairing = 0;          // pairing gates among them
+};
+
+Sweep sweep_executable(const std::vector<PhysGate> &g, const std::vector<char> &done, size_t first,
+                       uint64_t rmask, int n_positions, size_t window, bool collect) {
+  Sweep s;
+  uint8_t state[64] = {0};
+  int n_full = 0;
+  size_t seen = 0, last_pick = 0;
+  const size_t patience = 4 * (size_t)n_positions + 16;  // gates scanned without a pick before giving up
+  for (size_t i = first; i < g.size() && seen < window && n_full < n_positions; i++) {
+    if (done[i]) continue;
+    if (seen - last_pick > patience) break;
+    seen++;
+    const PhysGate &x = g[i];
+    if (x.c.kind == GK_NOP) {
+      if (collect) s.picked.push_back((int)i);
+      continue;
+    }
+    const bool pairing = is_pairing(x.c.kind);
+    bool ok = pairing ? (((rmask >> x.tpos) & 1ull) && state[x.tpos] == 0) : state[x.tpos] <= 1;
+    if (ok && x.cpos >= 0 && state[x.cpos] > 1) ok = false;
+    if (ok) {
+      if (collect) s.picked.push_back((int)i);
+      s.pairing += pairing ? 1 : 0;
+      last_pick = seen;
+      continue;
+    }
+    const uint8_t t_use = pairing ? 2 : 1;
+    if (state[x.tpos] < t_use) {
+      if (t_use == 2) n_full++;
+      state[x.tpos] = t_use;
+    }
+    if (x.cpos >= 0 && state[x.cpos] < 1) state[x.cpos] = 1;
+  }
+  return s;
+}
+
+std::vector<PassPlan> plan_passes_reordered(const std::vector<PhysGate> &gates, const PlannerConfig &cfg_in) {
+  PlannerConfig cfg = cfg_in;
+  cfg.compute_bound_flops = 1e30;  // the tile is chosen here, not by the builder's growth rule
+  const int n_positions = cfg.n_local + cfg.rank_bits;
+  const size_t window = 4096;
+  std::vector<PassPlan> out;
+  std::vector<char> done(gates.size(), 0);
+  size_t first = 0, left = gates.size();
+  int carry_api = 0;
+  while (left > 0) {
+    while (first < gates.size() && done[first]) first++;
+    std::unique_ptr<PassBuilder> b(new PassBuilder(cfg));
+    uint64_t tile_mask = 0;
+    int tile_size = 0;
+    for (int p = 0; p < cfg.fixed_low && p < cfg.n_local; p++) {
+      tile_mask |= 1ull << p;
+      tile_size++;
+    }
+    bool closed = false;
+    size_t taken = 0;
+    for (int seg = 0; seg < cfg.reorder_segments && !closed; seg++) {
+      // register set of this segment: grown one position at a time by marginal gain
+      uint64_t rmask = 0;
+      int base_pairing = 0;
+      for (int k = 0; k < cfg.reg_bits; k++) {
+        int best = -1, best_gain = 0;
+        bool best_in_tile = false;
+        for (int q = 0; q < cfg.n_local; q++) {
+          if ((rmask >> q) & 1ull) continue;
+          const bool in_tile = (tile_mask >> q) & 1ull;
+          if (!in_tile && tile_size + __builtin_popcountll(rmask & ~tile_mask) >= cfg.tile_bits_max) continue;
+          const int gain = sweep_executable(gates, done, first, rmask | (1ull << q), n_positions, window, false).pairing -
+                           base_pairing;
+          // ties: a position the tile already holds (keeps the tile small / leaves room), then the lowest
+          if (gain > best_gain || (gain == best_gain && gain > 0 && in_tile && !best_in_tile)) {
+            best = q;
+            best_gain = gain;
+            best_in_tile = in_tile;
+          }
+        }
+        if (best < 0) break;
+        rmask |= 1ull << best;
+        base_pairing += best_gain;
+      }
+      Sweep sw = sweep_executable(gates, done, first, rmask, n_positions, window, true);
+      if (sw.picked.empty()) break;
+      size_t added = 0;
+      for (int i : sw.picked) {
+        if (gates[(size_t)i].c.kind != GK_NOP && !b->fits(gates[(size_t)i])) {
+          closed = true;  // descriptor full: the rest of this sweep stays pending, in order
+          break;
+        }
+        b->add(gates[(size_t)i]);
+        done[(size_t)i] = 1;
+        added++;
+      }
+      taken += added;
+      left -= added;
+      for (int p : b->tile)
+        if (!((tile_mask >> p) & 1ull)) {
+          tile_mask |= 1ull << p;
+          tile_size++;
+        }
+      if (rmask == 0) break;  // nothing left to pair in reach: only diagonal gates were pending
+    }
+    if (taken == 0) {
+      // cannot happen (the first pending gate is always executable with its own target as register
+      // bit); never loop forever on a planner bug
+      b.reset(new PassBuilder(cfg));
+      b->add(gates[first]);
+      done[first] = 1;
+      left--;
+    }
+    if (!b->gates.empty()) {
+      PassPlan plan = b->close();
+      plan.n_gates_api += carry_api;  // value-preserving gates met before the first real one
+      carry_api = 0;
+      out.push_back(plan);
+    } else {
+      carry_api += b->n_api;
+    }
+  }
+  if (carry_api && !out.empty()) out.back().n_gates_api += carry_api;
+  return out;
+}
+
+}  // namespace
+
 std::vector<PassPlan> plan_passes(const std::vector<PhysGate> &gates_in, const PlannerConfig &cfg) {
   std::vector<PassPlan> out;
   std::vector<PhysGate> gates = gates_in;
   if (cfg.fast_math)
     for (PhysGate &g : gates) g.c.flops_per_amp = fast_flops(g);
+  if (cfg.fast_math && cfg.reorder) return plan_passes_reordered(gates, cfg);
   PassBuilder *b = new PassBuilder(cfg);
   for (const PhysGate &g : gates) {
     if (g.c.kind != GK_NOP && !b->fits(g)) {

@@ -7,6 +7,8 @@
 // the deferred queue and cuts it, IN ORDER, into passes and segments
 // (common.h).  Gates are never reordered or algebraically merged, so the
 // arithmetic each amplitude sees is the reference's, operation by operation.
+// (The opt-in math=fast mode gives that up: FMA arithmetic, fan tables and --
+// PlannerConfig::reorder -- commuting gates scheduled out of order.)
 #pragma once
 #include <string>
 #include <vector>
@@ -55,6 +57,10 @@ struct PlannerConfig {
   double compute_bound_flops = 90.0;      // flops per amplitude above which a pass is FP64-bound
   bool fast_math = false;   // math=fast: plan for the fused-multiply-add interpreter -- cost estimates count
                             // FMA instructions, fan entries carry product tables (write_fan_tables)
+  bool reorder = false;     // math=fast only: gates that commute (every shared qubit is a control or a diagonal
+                            // target of both) may trade places, so a pass is a SUBSEQUENCE of the queue
+                            // chosen to keep a tile busy over several circuit layers (plan_passes_reordered)
+  int reorder_segments = 8; // segments a reordered pass may spend before the next pass starts
   int fixed_low = QCS_LANE_BITS;  // positions 0..fixed_low-1 belong to every tile: global rows of
                             // 16 << fixed_low contiguous bytes; the remaining tile bits are free
 };

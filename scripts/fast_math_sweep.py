@@ -38,7 +38,13 @@ for math in ("exact", "fast"):
         for cbf in cbfs:
             tag = f"{math}/t{tb}/cbf{cbf:g}"
             os.environ["QCS_CUDA_COMPUTE_BOUND_FLOPS"] = repr(cbf)
-            run(n, [("qft",)], f"qft {tag}", math=math, tile_bits=tb)
-            run(n, po.random_circuit_script(n, 8), f"random_d8 {tag}", reps=1, math=math, tile_bits=tb)
+            run(n, [("qft",)], f"qft {tag}", math=math, tile_bits=tb, reorder="off")
+            run(n, po.random_circuit_script(n, 8), f"random_d8 {tag}", reps=1, math=math, tile_bits=tb, reorder="off")
     run(n, [("rz", q, 0.1 * q) for q in range(n)], f"rz_all {math}", math=math)
     run(n, [("h", q) for q in range(n)], f"h_all {math}", math=math)
+os.environ.pop("QCS_CUDA_COMPUTE_BOUND_FLOPS", None)
+for tb in tiles:
+    for segs in (4, 6, 8, 12):
+        tag = f"fast+reorder/t{tb}/segs{segs}"
+        run(n, po.random_circuit_script(n, 8), f"random_d8 {tag}", reps=1, math="fast", tile_bits=tb, reorder_segments=segs)
+    run(n, [("qft",)], f"qft fast+reorder/t{tb}", math="fast", tile_bits=tb)

@@ -54,14 +54,15 @@ def _check(got, want, what=""):
     return err.max() / scale
 
 
+@pytest.mark.parametrize("reorder", ["on", "off"])
 @pytest.mark.parametrize("tile_bits", [10, 11, 12])
 @pytest.mark.parametrize("n", [10, 11, 12, 13, 15, 17, 21])
-def test_fast_random_circuits_within_tolerance(n, tile_bits):
+def test_fast_random_circuits_within_tolerance(n, tile_bits, reorder):
     rng = np.random.default_rng(4000 + n)
     for trial in range(3 if n < 20 else 1):
         script = _random_script(rng, n, 60 + 40 * trial)
         init = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
-        orc = po.Oracle(n, "corrected"); c = Circuit(n, tile_bits=tile_bits)
+        orc = po.Oracle(n, "corrected"); c = Circuit(n, tile_bits=tile_bits, reorder=reorder)
         orc.load_state(init); c.load_state(init)
         po.replay(orc, script); po.replay(c, script)
         _check(c.state(), orc.state(), f"n={n} trial={trial}\n{c.describe_plan()[:1500]}")
@@ -70,15 +71,16 @@ def test_fast_random_circuits_within_tolerance(n, tile_bits):
         orc.close(); c.close()
 
 
+@pytest.mark.parametrize("reorder", ["on", "off"])
 @pytest.mark.parametrize("tile_bits", [10, 11, 12])
 @pytest.mark.parametrize("n", [12, 14, 16, 20])
-def test_fast_qft_and_fans(n, tile_bits):
+def test_fast_qft_and_fans(n, tile_bits, reorder):
     """Dense start state so every controlled phase acts; fans of all lengths, consecutive and scattered controls."""
     rng = np.random.default_rng(n)
     init = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
     init /= np.linalg.norm(init)
     for name, script in (("qft", [("qft",)]), ("qft.qft", [("qft",), ("qft",)]), ("fans", _fan_script(n, n))):
-        orc = po.Oracle(n, "corrected"); c = Circuit(n, tile_bits=tile_bits)
+        orc = po.Oracle(n, "corrected"); c = Circuit(n, tile_bits=tile_bits, reorder=reorder)
         orc.load_state(init); c.load_state(init)
         po.replay(orc, script); po.replay(c, script)
         _check(c.state(), orc.state(), f"{name} n={n}\n{c.describe_plan()[:1500]}")
@@ -109,6 +111,26 @@ def test_fast_every_target_control_pair(tile_bits):
                     orc.apply_c1q(m, ctl, t); c.apply_c1q(m, ctl, t)
         _check(c.state(), orc.state(), cls)
         orc.close(); c.close()
+
+
+def test_fast_brickwork_deep_passes():
+    """BASELINE config 5's circuit shape at 24 qubits, depth 12: the reordered plan (a pass follows its
+    tile through several layers) needs under half the passes of the in-order plan and computes the
+    same state within tolerance."""
+    n = 24
+    script = po.random_circuit_script(n, 12)
+    orc = po.Oracle(n, "corrected")
+    po.replay(orc, script)
+    want = orc.state()
+    orc.close()
+    passes = {}
+    for reorder in ("on", "off"):
+        c = Circuit(n, reorder=reorder)
+        po.replay(c, script)
+        _check(c.state(), want, f"reorder={reorder}")
+        passes[reorder] = c.stats()["passes"]
+        c.close()
+    assert passes["on"] * 2 < passes["off"], passes
 
 
 def test_fast_measurement_and_shots_follow_the_state():
