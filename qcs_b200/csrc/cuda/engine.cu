@@ -288,9 +288,8 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
   cfg.fixed_low = e.opt.fixed_low;
   cfg.compute_bound_flops = e.opt.compute_bound_flops;
   cfg.fast_math = e.opt.fast_math;
-  // sharded engines cut the queue at position swaps and hoist those onto passes by queue index
-  // (run_range): their passes stay in queue order
-  cfg.reorder = e.opt.fast_math && e.opt.reorder && !dist().active;
+  // (sharded engines: run_range_reordered keeps track of which gates a pass took)
+  cfg.reorder = e.opt.fast_math && e.opt.reorder;
   cfg.reorder_segments = e.opt.reorder_segments;
   cfg.tile_bits_min = min_tile_bits(e);
   cfg.tile_bits_max = std::max(cfg.tile_bits_min, std::min(e.opt.tile_bits, e.nl));
@@ -453,7 +452,77 @@ static bool can_fuse_swaps(const Engine &e) {
 // folded into the stores of a pass that runs anyway -- the EARLIEST pass after the victim
 // position's last pairing use, so that the NVLink transfer hides behind as much arithmetic as
 // possible and later swaps find later passes free.
+static bool reorder_enabled(const Engine &e) {
+  return e.opt.fast_math && e.opt.reorder && e.opt.fusion && e.nl >= min_tile_bits(e);
+}
+
+// math=fast with reordering on a sharded engine.  The planner gets the WHOLE pending queue: it runs
+// everything the current layout allows, several layers deep where qubits do not depend on a global
+// one, and leaves out the pairing gates on global positions and what hangs on them (planner.h).
+// Then one global qubit is swapped in.  Same policy as run_range below -- the swap rides on the
+// stores of the earliest pass after which nothing pairs on the victim position -- but "the gates that
+// have run" is a set, not a prefix: they are taken out of the pending list by index, and what is left
+// (in queue order) is planned again under the new layout.
+static int run_range_reordered(Engine &e, const std::vector<HostGate> &q, size_t begin, size_t end) {
+  const bool fuse = can_fuse_swaps(e);
+  std::vector<HostGate> pend(q.begin() + (long)begin, q.begin() + (long)end);
+  while (!pend.empty()) {
+    std::vector<PhysGate> batch;
+    for (const HostGate &g : pend) batch.push_back(to_phys(e, g));
+    std::vector<PassPlan> plan = plan_batch(e, batch);
+    std::vector<char> planned(pend.size(), 0);
+    for (const PassPlan &p : plan)
+      for (int id : p.api_ids) planned[(size_t)id] = 1;
+    std::vector<HostGate> rest;  // what cannot run under this layout, in queue order
+    for (size_t i = 0; i < pend.size(); i++)
+      if (!planned[i]) rest.push_back(pend[i]);
+    if (rest.empty()) {
+      if (e.opt.dryrun) trace_gates(e, batch);
+      return launch_passes(e, plan, 0, plan.size(), nullptr);
+    }
+    // the first gate left behind pairs on a global position (anything else would have been taken)
+    const PhysGate blocker = to_phys(e, rest[0]);
+    if (!(is_pairing_kind(blocker.c.kind) && blocker.tpos >= e.nl))
+      return set_error(QCS_CUDA_ERR_CUDA, "internal: scheduler left a runnable gate behind");
+    const int gpos = blocker.tpos;
+    const int victim = pick_victim(e, rest, 0, 0, fuse ? e.opt.min_fused_victim : QCS_LANE_BITS);
+    size_t chosen = 0;  // last pass that pairs on the victim position (the first pass if none does)
+    for (size_t k = 0; k < plan.size(); k++) {
+      const PassParams &pp = plan[k].params;
+      for (int gi = 0; gi < pp.n_gates; gi++)
+        if (!(pp.gate[gi].flags & GF_FAN_HEADER) && is_pairing_kind(pp.gate[gi].kind) &&
+            pp.gate[gi].tpos == victim)
+          chosen = k;
+    }
+    SwapStore sw{};
+    const bool ride = fuse && !plan.empty() && (e.opt.dryrun || dist_fused_swap_args(e, victim, gpos, sw));
+    const size_t n_run = plan.empty() ? 0 : (ride ? chosen + 1 : plan.size());
+    std::vector<char> ran(pend.size(), 0);
+    std::vector<PhysGate> ran_gates;
+    for (size_t k = 0; k < n_run; k++)
+      for (int id : plan[k].api_ids) {
+        ran[(size_t)id] = 1;
+        ran_gates.push_back(batch[(size_t)id]);
+      }
+    if (e.opt.dryrun) trace_gates(e, ran_gates);
+    if (ride) {
+      RC(launch_passes(e, plan, 0, n_run, &sw));
+      note_swap(e, victim, gpos);
+      e.fused_swaps++;
+    } else {
+      RC(launch_passes(e, plan, 0, n_run, nullptr));  // nothing to ride on, or no peer mapping
+      RC(swap_positions(e, victim, gpos));
+    }
+    size_t w = 0;
+    for (size_t i = 0; i < pend.size(); i++)
+      if (!ran[i]) pend[w++] = pend[i];
+    pend.resize(w);
+  }
+  return QCS_CUDA_OK;
+}
+
 static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, size_t end) {
+  if (dist().active && reorder_enabled(e)) return run_range_reordered(e, q, begin, end);
   const bool fuse = can_fuse_swaps(e);
   size_t i = begin;
   while (i < end) {

@@ -206,6 +206,7 @@ struct PassBuilder {
   const PlannerConfig &cfg;
   std::vector<int> tile;          // physical positions in the tile (unsorted until close)
   std::vector<PhysGate> gates;
+  std::vector<int> ids;           // input indices of everything add()ed, NOPs included
   int n_api = 0;
   double flops = 0.0;
 
@@ -264,8 +265,9 @@ struct PassBuilder {
     return true;
   }
 
-  void add(const PhysGate &g) {
+  void add(const PhysGate &g, int id) {
     n_api++;
+    ids.push_back(id);
     if (g.c.kind == GK_NOP) return;
     if (is_pairing(g.c.kind) && !has(g.tpos)) tile.push_back(g.tpos);
     gates.push_back(g);
@@ -516,6 +518,7 @@ struct PassBuilder {
       pp.n_tile_runs = n_runs;  // <= 8: seven tile bits above position 4 split the rest into <= 8 runs
     }
     plan.n_gates_api = n_api;
+    plan.api_ids = ids;
     plan.flops_per_amp = flops;
     return plan;
   }
@@ -583,7 +586,7 @@ std::vector<PassPlan> plan_passes_reordered(const std::vector<PhysGate> &gates, 
   std::vector<PassPlan> out;
   std::vector<char> done(gates.size(), 0);
   size_t first = 0, left = gates.size();
-  int carry_api = 0;
+  std::vector<int> carry_ids;
   while (left > 0) {
     while (first < gates.size() && done[first]) first++;
     std::unique_ptr<PassBuilder> b(new PassBuilder(cfg));
@@ -627,7 +630,7 @@ std::vector<PassPlan> plan_passes_reordered(const std::vector<PhysGate> &gates, 
           closed = true;  // descriptor full: the rest of this sweep stays pending, in order
           break;
         }
-        b->add(gates[(size_t)i]);
+        b->add(gates[(size_t)i], i);
         done[(size_t)i] = 1;
         added++;
       }
@@ -641,23 +644,30 @@ std::vector<PassPlan> plan_passes_reordered(const std::vector<PhysGate> &gates, 
       if (rmask == 0) break;  // nothing left to pair in reach: only diagonal gates were pending
     }
     if (taken == 0) {
-      // cannot happen (the first pending gate is always executable with its own target as register
-      // bit); never loop forever on a planner bug
+      // The first pending gate pairs on a position this shard does not hold: nothing more can run
+      // under the current layout.  The caller swaps the position in and plans the rest again.
+      if (is_pairing(gates[first].c.kind) && gates[first].tpos >= cfg.n_local) break;
+      // cannot happen otherwise (the first pending gate is always executable with its own target as
+      // register bit); never loop forever on a planner bug
       b.reset(new PassBuilder(cfg));
-      b->add(gates[first]);
+      b->add(gates[first], (int)first);
       done[first] = 1;
       left--;
     }
     if (!b->gates.empty()) {
       PassPlan plan = b->close();
-      plan.n_gates_api += carry_api;  // value-preserving gates met before the first real one
-      carry_api = 0;
+      plan.n_gates_api += (int)carry_ids.size();  // value-preserving gates met before the first real one
+      plan.api_ids.insert(plan.api_ids.begin(), carry_ids.begin(), carry_ids.end());
+      carry_ids.clear();
       out.push_back(plan);
     } else {
-      carry_api += b->n_api;
+      carry_ids.insert(carry_ids.end(), b->ids.begin(), b->ids.end());
     }
   }
-  if (carry_api && !out.empty()) out.back().n_gates_api += carry_api;
+  if (!carry_ids.empty() && !out.empty()) {
+    out.back().n_gates_api += (int)carry_ids.size();
+    out.back().api_ids.insert(out.back().api_ids.end(), carry_ids.begin(), carry_ids.end());
+  }
   return out;
 }
 
@@ -670,18 +680,20 @@ std::vector<PassPlan> plan_passes(const std::vector<PhysGate> &gates_in, const P
     for (PhysGate &g : gates) g.c.flops_per_amp = fast_flops(g);
   if (cfg.fast_math && cfg.reorder) return plan_passes_reordered(gates, cfg);
   PassBuilder *b = new PassBuilder(cfg);
-  for (const PhysGate &g : gates) {
+  for (size_t i = 0; i < gates.size(); i++) {
+    const PhysGate &g = gates[i];
     if (g.c.kind != GK_NOP && !b->fits(g)) {
       out.push_back(b->close());
       delete b;
       b = new PassBuilder(cfg);
     }
-    b->add(g);
+    b->add(g, (int)i);
   }
   if (!b->gates.empty()) {
     out.push_back(b->close());
   } else if (b->n_api > 0 && !out.empty()) {
     out.back().n_gates_api += b->n_api;  // trailing NOPs ride on the previous pass
+    out.back().api_ids.insert(out.back().api_ids.end(), b->ids.begin(), b->ids.end());
   }
   delete b;
   return out;

@@ -39,6 +39,8 @@ Classified classify_gate(const double m[8], bool controlled, Semantics sem);
 struct PassPlan {
   PassParams params;
   int n_gates_api;          // API-level gates folded into this pass (incl. NOPs)
+  std::vector<int> api_ids; // which ones: indices into plan_passes()'s input, in execution order
+                            // (consecutive unless PlannerConfig::reorder)
   int n_fan_headers = 0;    // fan header records among params.n_gates (not gates)
   double flops_per_amp;     // planner's cost estimate
   std::vector<int> tile_positions;
@@ -74,6 +76,8 @@ struct PhysGate {
   int cpos;
 };
 
+// With PlannerConfig::reorder the input may contain pairing gates on GLOBAL positions: they (and
+// whatever depends on them) are left out of every pass -- api_ids tells the caller what ran.
 std::vector<PassPlan> plan_passes(const std::vector<PhysGate> &gates,
                                   const PlannerConfig &cfg);
 

@@ -80,9 +80,11 @@ def main():
     assert C.qcs_cuda_dist_init_plan_only(rank, world) == 0, _ffi.last_error()
     from tests.test_dist_gloo import CASES
     failures = []
-    for name, (n, sem, script) in CASES.items():
+    for name, case in CASES.items():
+        n, sem, script = case[:3]
+        extra = case[3] if len(case) > 3 else {}
         nl = n - (world.bit_length() - 1)
-        c = Circuit(n, dryrun=True, semantics=sem)
+        c = Circuit(n, dryrun=True, semantics=sem, **extra)
         po.replay(c, script)
         c.flush()
         trace, perm = c.trace(), c.layout()
@@ -116,8 +118,13 @@ def main():
             orc = po.Oracle(n, sem)
             po.replay(orc, script)
             want = orc.state()
-            if not np.all(got == want):
-                failures.append(f"{name}: {int(np.sum(got != want))} amplitudes differ (swaps={n_swaps})")
+            if extra.get("math") == "fast":  # gates run in a different (commuting) order: rounding differs
+                same = bool(np.all(np.abs(got - want) <= 1e-12 * np.abs(want).max()))
+            else:
+                same = bool(np.all(got == want))
+            if not same:
+                failures.append(f"{name}: {int(np.sum(got != want))} amplitudes differ, max |delta| "
+                                f"{np.abs(got - want).max():.3e} (swaps={n_swaps})")
             else:
                 print(f"ok {name}: n={n} world={world} swaps={n_swaps} layout={perm}", flush=True)
         c.close()

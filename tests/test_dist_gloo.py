@@ -27,6 +27,15 @@ CASES = {
     "random_brickwork": (14, "corrected", random_circuit_script(14, 6, seed=77)),
     "random_brickwork_reference_semantics": (14, "reference", random_circuit_script(14, 4, seed=78)),
     "ghz_reference_semantics": (13, "reference", [("ghz",), ("h", 12), ("cnot", 12, 11)]),
+    # math=fast: passes are subsequences of the queue (commuting gates reordered), swaps ride on them;
+    # compared within 1e-12 instead of bit for bit (a 4th entry = extra engine options)
+    "fast_reordered_brickwork": (14, "corrected", random_circuit_script(14, 8, seed=79), {"math": "fast", "tile_kernel": "ldg8"}),
+    "fast_reordered_brickwork_10bit_tiles": (15, "corrected", random_circuit_script(15, 6, seed=80),
+                                             {"math": "fast", "tile_kernel": "ldg8", "tile_bits": 10}),
+    "fast_reordered_qft": (13, "corrected", [("h", q) for q in range(13)] + [("ry", 12, 0.6), ("qft",)],
+                           {"math": "fast", "tile_kernel": "ldg8"}),
+    "fast_in_order_brickwork": (14, "corrected", random_circuit_script(14, 5, seed=81),
+                                {"math": "fast", "tile_kernel": "ldg8", "reorder": "off"}),
 }
 
 
