@@ -128,6 +128,15 @@ def op_diag_fast(r, er="dr", ei="di"):
             f"fma.rn.f64 qr{r}, {er}, qr{r}, t0;", f"fma.rn.f64 qi{r}, {er}, qi{r}, t1;"]
 
 
+def acc_thread_factor(er="dr", ei="di"):
+    """math=fast: (fr, fi) *= (er, ei).  (fr, fi) is the thread's pending scalar factor: a diagonal
+    gate whose target and control are NOT register bits multiplies all amplitudes of a thread by the
+    same number, which commutes with everything else a segment does to the thread's registers, so it
+    is multiplied up here and applied once when the segment ends (fused_body.inc, QCS3F_FLUSH_ASM)."""
+    return [f"mul.rn.f64 t0, fi, {ei};", f"mul.rn.f64 t1, fi, {er};", "neg.f64 t0, t0;",
+            f"fma.rn.f64 t2, fr, {er}, t0;", f"fma.rn.f64 fi, fr, {ei}, t1;", "mov.f64 fr, t2;"]
+
+
 def op_pair(kind, row0, a, b):
     """a = register with target bit 0, b = target bit 1.  Operation order = c_add(c_mul(g0,v0),
     c_mul(g1,v1)) (reference src/q_gates.c:140-141); row0 = reference-semantics controlled update."""
@@ -233,8 +242,11 @@ def emit(R, fast=False):
                 body += ["@!p bra DONE;", f"ld.param.f64 dr, [%1+{OFF_M(6)}];", f"ld.param.f64 di, [%1+{OFF_M(7)}];"]
             else:
                 body += ["@p bra DONE;", f"ld.param.f64 dr, [%1+{OFF_M(0)}];", f"ld.param.f64 di, [%1+{OFF_M(1)}];"]
-            for r in regs(R, c=c):
-                body += diag_body(r)
+            if fast and c < 0:
+                body += acc_thread_factor()
+            else:
+                for r in regs(R, c=c):
+                    body += diag_body(r)
             case(sym, body, c < 0)
     # diagonal, target = register bit t: id = 175 + (t*5 + creg+1)*3 + (halves-1)
     for t in range(R):
@@ -290,8 +302,11 @@ def emit(R, fast=False):
                      f"FS{n}:", "shr.u32 mask, mask, 4;", "shr.u32 wm, wm, 4;",
                      f"add.u64 ea, ea, {4 * E};", f"bra FL{n};",
                      f"FE{n}:", "setp.eq.u32 p, tst, 0;", f"@p bra FX{n};"]
-            for r in diag_regs:
-                body += op_diag_fast(r, "ar", "ai")
+            if t < 0:
+                body += acc_thread_factor("ar", "ai")
+            else:
+                for r in diag_regs:
+                    body += op_diag_fast(r, "ar", "ai")
             body += [f"FX{n}:", "add.s32 %0, %0, K;", "bra DONE;",
                      f"FG{n}:", "mov.u32 mask, 0;", "mov.u32 kidx, 0;", "mov.u64 ea, %1;",
                      f"FH{n}:", f"ld.param.u8 cs, [ea+{E + OFF_CPOS}];", "shr.u64 t64, %2, cs;",
@@ -337,8 +352,20 @@ def emit(R, fast=False):
         text.append(f"{name}:")
         text += body
     text += ["DONE:", "}"]
-    out = [f"#define {P}_REGS_ALL(OP) " + " ".join(f"OP({r})" for r in regs(R)),
-           f"#define {P}_DISPATCH_ASM \\"]
+    out = [f"#define {P}_REGS_ALL(OP) " + " ".join(f"OP({r})" for r in regs(R))]
+    if fast:
+        flush = ["{", ".reg .pred p, q;", ".reg .f64 t0, t1;",
+                 "setp.eq.f64 p, fr, 0d3FF0000000000000;", "setp.eq.f64 q, fi, 0d0000000000000000;",
+                 "and.pred p, p, q;", "@p bra FLUSHED;"]
+        for r in regs(R):
+            flush += op_diag_fast(r, "fr", "fi")
+        flush += ["FLUSHED:", "}"]
+        out.append(f"#define {P}_FLUSH_ASM \\")
+        for line in flush:
+            sep = "\\n" if line.endswith(":") or line in ("{", "}") else "\\n\\t"
+            out.append(f'  "{line}{sep}" \\')
+        out[-1] = out[-1][:-2]
+    out.append(f"#define {P}_DISPATCH_ASM \\")
     for line in text:
         sep = "\\n" if line.endswith(":") or line in ("{", "}") else "\\n\\t"
         out.append(f'  "{line}{sep}" \\')

@@ -205,6 +205,7 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 // ---------------------------------------------------------------------------
 // Kernel bodies, instantiated for R = 4 (16 amplitudes/thread) and R = 3 (8).
 // ---------------------------------------------------------------------------
+#define QCS_FAST 0
 #define QCS_R 4
 #define QCS_T 12
 #define QCS_CT (1 << (QCS_T - QCS_R))
@@ -261,7 +262,9 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 
 // math=fast: the same three ldg8 kernels around the fused-multiply-add interpreter (QCS3F_*)
 #undef QCS_LIST
+#undef QCS_FAST
 #define QCS_LIST(x) QCS3F_##x
+#define QCS_FAST 1
 #define QCS_WITH_TMA 0
 
 #define QCS_T 12
@@ -294,6 +297,7 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 #undef QCS_NREG_STR
 #undef QCS_LIST
 #undef QCS_WITH_LDG
+#undef QCS_FAST
 
 // How many tiles ahead a CTA prefetches into L2 (QCS_CUDA_PREFETCH; off by default).
 static uint32_t prefetch_distance() {
