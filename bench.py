@@ -371,10 +371,13 @@ def main() -> None:
     if world == 1 and not args.skip_aux:
         light = light_pass_aux(Circuit, kw, n)
     if not args.skip_aux:
-        fast = fast_math_aux(Circuit, kw, n, args.steps, warmup, world, barrier, dist, torch)
-        if aux is not None:
-            kf = dict(kw); kf["math"] = "fast"
-            fast["random_circuit"] = random_circuit_aux(Circuit, kf, world, barrier, dist, torch)
+        try:  # an aux report must never cost the headline line
+            fast = fast_math_aux(Circuit, kw, n, args.steps, warmup, world, barrier, dist, torch)
+            if aux is not None:
+                kf = dict(kw); kf["math"] = "fast"
+                fast["random_circuit"] = random_circuit_aux(Circuit, kf, world, barrier, dist, torch)
+        except Exception as exc:
+            fast = {"failed": repr(exc)}
 
     if rank != 0:
         if world > 1:

@@ -71,6 +71,13 @@ static inline int qcs_op_id_diag_reg(int treg, int creg, int halves) {
 #define QCS_OP_FAN_BASE 240
 #define QCS_MAX_FAN_ENTRIES 32
 #define QCS_MAX_PASS_FANS 48
+// math=fast only.  Header of a UNIFORM fan, op = QCS_OP_UFAN_BASE + treg + 1: same record layout as a
+// fan, but every entry is controlled by a position outside the tile (a non-tile local position or a
+// rank bit), so the product of the phases is one number for the whole CTA.  One thread per uniform
+// fan computes it in the kernel prologue (while the tile's loads are in flight) into shared-memory
+// slot `csel`; the interpreter fetches it with one ld.shared.  PassParams::ufan_header lists the
+// headers.  (QFT: 20 of the 29 controls of the first target are outside a 10-bit tile.)
+#define QCS_OP_UFAN_BASE 248
 // or-ed into a pairing / diagonal id: the gate's control is a bit the thread tests once for all its
 // amplitudes (a lane / warp tile bit, a position outside the tile, a rank bit); csel = its position
 #define QCS_OP_TCTL 0x100
@@ -128,4 +135,9 @@ struct PassParams {
   uint64_t goff[2][QCS_MAX_REG_BITS];  // [first/last][register role bit]
   DSegment seg[QCS_MAX_PASS_SEGMENTS];
   DGate gate[QCS_MAX_PASS_GATES + QCS_MAX_PASS_FANS];  // gates + fan headers
+  // math=fast: record indices of the uniform-fan headers (QCS_OP_UFAN_BASE); slot k of the kernel's
+  // shared-memory factor table belongs to ufan_header[k]
+  uint16_t ufan_header[QCS_MAX_PASS_FANS];
+  int32_t n_ufans;
+  int32_t pad_;
 };

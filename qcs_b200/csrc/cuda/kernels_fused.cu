@@ -352,7 +352,8 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
     sm_count = sms;
   }
   const size_t smem_tma = (size_t)kSlots * kTileBytes + 128;  // slots + barriers + tile origins
-  const size_t smem_ldg = (size_t)16 << T;
+  // math=fast: the tile + one 16-byte factor per uniform fan behind it
+  const size_t smem_ldg = ((size_t)16 << T) + (fast ? 16 * QCS_MAX_PASS_FANS : 0);
   // 3, 4, 5: ldg8 at 12, 11, 10 bits; 6, 7, 8: the same with math=fast
   const int slot = variant == 3 ? 3 + (QCS_TILE_BITS - T) + (fast ? 3 : 0) : variant;
   if (!configured[slot]) {

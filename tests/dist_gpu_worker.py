@@ -39,7 +39,27 @@ def main():
             print(f"[rank {rank}] FAIL {msg}", flush=True)
 
     for fusion, exchange in (("on", "p2p"), ("on", "nccl"), ("off", "p2p")):
-        for name, (n, sem, script) in CASES.items():
+        for name, case in CASES.items():
+            n, sem, script = case[:3]
+            extra = case[3] if len(case) > 3 else {}
+            if extra.get("math") == "fast":
+                # opt-in tolerance mode (reordered schedule, FMA arithmetic): 1e-12, fused kernels only
+                if fusion != "on":
+                    continue
+                c = Circuit(n, semantics=sem, fusion=fusion, exchange=exchange, **extra)
+                orc = po.Oracle(n, sem)
+                po.replay(c, script); po.replay(orc, script)
+                c.flush(); st = c.stats()
+                first, count = c._shard()
+                got = c.state(); full = orc.state(); want = full[first:first + count]
+                check(np.all(np.abs(got - want) <= 1e-12 * np.abs(full).max()),
+                      f"{name}/{exchange}: max |delta| {np.abs(got - want).max():.3e}")
+                check(abs(c.get_probability(5) - orc.get_probability(5)) <= 1e-12, f"{name}: prob")
+                if rank == 0:
+                    print(f"done {name}/{fusion}/{exchange}: passes={st['passes']} remaps={st['remaps']} "
+                          f"fused={st['fused_remaps']}", flush=True)
+                c.close(); orc.close()
+                continue
             c = Circuit(n, semantics=sem, fusion=fusion, exchange=exchange)
             orc = po.Oracle(n, sem)
             po.replay(c, script); po.replay(orc, script)
@@ -80,6 +100,19 @@ def main():
             check((st["fused_remaps"] > 0) == (fuse == "on"), f"{name}/fuse_swaps={fuse}: fused_remaps={st['fused_remaps']}")
             if rank == 0:
                 print(f"done {name}/fuse_swaps={fuse}: passes={st['passes']} remaps={st['remaps']} "
+                      f"fused={st['fused_remaps']}", flush=True)
+            c.close()
+        # the same circuit in math=fast: whole-queue reordered schedule, swaps riding on its passes
+        full = orc.state()
+        for fuse in ("on", "off"):
+            c = Circuit(n, semantics="corrected", fuse_swaps=fuse, math="fast", tile_kernel="ldg8")
+            po.replay(c, script); c.flush(); st = c.stats()
+            first, count = c._shard()
+            got = c.state(); want = full[first:first + count]
+            check(np.all(np.abs(got - want) <= 1e-12 * np.abs(full).max()),
+                  f"{name}/fast/fuse_swaps={fuse}: max |delta| {np.abs(got - want).max():.3e}")
+            if rank == 0:
+                print(f"done {name}/fast/fuse_swaps={fuse}: passes={st['passes']} remaps={st['remaps']} "
                       f"fused={st['fused_remaps']}", flush=True)
             c.close()
         orc.close()
