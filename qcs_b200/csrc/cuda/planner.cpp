@@ -377,7 +377,7 @@ struct PassBuilder {
     auto case_label = [&](int sym) -> uint16_t {
       return cfg.reg_bits == 3 ? QCS3_CASE_LABEL[sym] : QCS4_CASE_LABEL[sym];
     };
-    int out_n = 0, n_fans = 0, fan_left = 0;
+    int out_n = 0, n_fans = 0;
     for (int si = 0; si < (int)segs.size(); si++) {
       DSegment &ds = pp.seg[si];
       {
@@ -393,38 +393,9 @@ struct PassBuilder {
           if (tbit >= 0 && segs[si].regbits[k] == tbit) return k;
         return -1;
       };
-      for (int gi = segs[si].begin; gi < segs[si].end; gi++) {
-        const PhysGate &g = gates[gi];
+      // writes the record of one gate
+      auto emit_record = [&](const PhysGate &g) {
         const int treg = reg_of(g.tpos), creg = reg_of(g.cpos);
-        // Controlled-phase fan: a run of consecutive controlled diag(1, e^{ia}) gates on one target
-        // whose controls are not register bits gets a header so the kernel walks it in a tight
-        // loop (QFT: one or two fans per round).  Entries controlled by a register bit stay
-        // ordinary gates and split the run.
-        auto fan_entry = [&](const PhysGate &x) { return is_cphase(x) && reg_of(x.cpos) < 0; };
-        if (fan_left == 0 && fan_entry(g) && n_fans < QCS_MAX_PASS_FANS) {
-          int run = 1;
-          bool consecutive = true;
-          while (gi + run < segs[si].end && fan_entry(gates[gi + run]) &&
-                 gates[gi + run].tpos == g.tpos && run < QCS_MAX_FAN_ENTRIES) {
-            if (gates[gi + run].cpos != g.cpos + run) consecutive = false;
-            run++;
-          }
-          if (run >= 2) {
-            DGate &hd = pp.gate[out_n++];
-            std::memset(&hd, 0, sizeof(hd));
-            hd.op = case_label(QCS_OP_FAN_BASE + treg + 1);
-            hd.kind = GK_DIAG;
-            hd.flags = GF_FAN_HEADER;
-            hd.csel = consecutive ? (uint8_t)g.cpos : 0xFF;
-            hd.tsel = (uint8_t)run;  // number of entries that follow
-            hd.tpos = (int8_t)g.tpos;
-            hd.cpos = (int8_t)g.cpos;
-            hd.treg_creg = (uint8_t)(treg + 1);
-            n_fans++;
-            fan_left = run;
-          }
-        }
-        if (fan_left > 0) fan_left--;
         DGate &dg = pp.gate[out_n++];
         std::memset(&dg, 0, sizeof(dg));
         std::memcpy(dg.m, g.c.m, sizeof(dg.m));
@@ -459,6 +430,69 @@ struct PassBuilder {
         }
         if (op != QCS_OP_NONE && thread_ctl) op |= QCS_OP_TCTL;
         dg.op = case_label(op);
+      };
+      // writes a fan header for the `count` entries that follow; uniform = every control outside the tile
+      auto emit_fan_header = [&](const PhysGate &first, int count, bool consecutive, bool uniform) {
+        const int treg = reg_of(first.tpos);
+        const int h = out_n;
+        DGate &hd = pp.gate[out_n++];
+        std::memset(&hd, 0, sizeof(hd));
+        hd.op = case_label((uniform ? QCS_OP_UFAN_BASE : QCS_OP_FAN_BASE) + treg + 1);
+        hd.kind = GK_DIAG;
+        hd.flags = GF_FAN_HEADER;
+        hd.csel = uniform ? (uint8_t)pp.n_ufans : (consecutive ? (uint8_t)first.cpos : 0xFF);
+        hd.tsel = (uint8_t)count;  // number of entries that follow
+        hd.tpos = (int8_t)first.tpos;
+        hd.cpos = (int8_t)first.cpos;
+        hd.treg_creg = (uint8_t)(treg + 1);
+        hd.pad[0] = consecutive ? 1 : 0;  // uniform fans: entry k is controlled by position cpos + k
+        if (uniform) pp.ufan_header[pp.n_ufans++] = (uint16_t)h;
+        n_fans++;
+      };
+      // Controlled-phase fan: a run of consecutive controlled diag(1, e^{ia}) gates on one target
+      // whose controls are not register bits gets a header so the kernel walks it in a tight loop
+      // (QFT: one or two fans per round).  Entries controlled by a register bit stay ordinary gates
+      // and split the run.
+      auto fan_entry = [&](const PhysGate &x) { return is_cphase(x) && reg_of(x.cpos) < 0; };
+      for (int gi = segs[si].begin; gi < segs[si].end; gi++) {
+        const PhysGate &g = gates[gi];
+        if (fan_entry(g) && n_fans + (cfg.fast_math ? 2 : 1) <= QCS_MAX_PASS_FANS) {
+          int run = 1;
+          while (gi + run < segs[si].end && fan_entry(gates[gi + run]) &&
+                 gates[gi + run].tpos == g.tpos && run < QCS_MAX_FAN_ENTRIES)
+            run++;
+          if (run >= 2 && !cfg.fast_math) {
+            bool consecutive = true;
+            for (int k = 1; k < run; k++)
+              if (gates[gi + k].cpos != g.cpos + k) consecutive = false;
+            emit_fan_header(g, run, consecutive, false);
+            for (int k = 0; k < run; k++) emit_record(gates[gi + k]);
+            gi += run - 1;
+            continue;
+          }
+          if (run >= 2) {
+            // math=fast: the entries commute (all diagonal), so the run is sorted into the entries a
+            // thread decides for itself (control on a tile bit) and the ones the whole CTA shares
+            // (control outside the tile: common.h QCS_OP_UFAN_BASE); each part of two or more entries
+            // becomes a fan, single entries stay ordinary gates
+            std::vector<int> own, shared;
+            for (int k = 0; k < run; k++)
+              (tilebit_of(gates[gi + k].cpos) >= 0 ? own : shared).push_back(gi + k);
+            for (int part = 0; part < 2; part++) {
+              const std::vector<int> &ids = part == 0 ? own : shared;
+              if (ids.size() >= 2) {
+                bool consecutive = true;
+                for (size_t k = 1; k < ids.size(); k++)
+                  if (gates[ids[k]].cpos != gates[ids[0]].cpos + (int)k) consecutive = false;
+                emit_fan_header(gates[ids[0]], (int)ids.size(), consecutive, part == 1);
+              }
+              for (int id : ids) emit_record(gates[id]);
+            }
+            gi += run - 1;
+            continue;
+          }
+        }
+        emit_record(g);
       }
       ds.gate_end = (uint16_t)out_n;
     }

@@ -46,7 +46,9 @@ class PassParams(ctypes.Structure):
                 ("n_segments", ctypes.c_int32), ("n_gates", ctypes.c_int32),
                 ("reg_bits", ctypes.c_int32), ("n_tile_runs", ctypes.c_int32),
                 ("tile_run", DTileRun * 12), ("goff", (ctypes.c_uint64 * MAX_REG_BITS) * 2),
-                ("seg", DSegment * MAX_SEGMENTS), ("gate", DGate * (MAX_GATES + MAX_FANS))]
+                ("seg", DSegment * MAX_SEGMENTS), ("gate", DGate * (MAX_GATES + MAX_FANS)),
+                ("ufan_header", ctypes.c_uint16 * MAX_FANS), ("n_ufans", ctypes.c_int32),
+                ("pad_", ctypes.c_int32)]
 
 
 def read_plan(circuit):
@@ -84,7 +86,7 @@ def _apply_gate(state, idx, g):
         state[i1] = m[2] * v0 + m[3] * v1
 
 
-def _apply_fast_fan(state, idx, gates, h):
+def _apply_fast_fan(state, idx, gates, h, uniform=False):
     """A fan the way the math=fast kernel walks it: the thread's participation mask, then one table
     lookup per group of four entries, then ONE multiplication of the amplitudes with target bit 1."""
     hd = gates[h]
@@ -92,8 +94,10 @@ def _apply_fast_fan(state, idx, gates, h):
     mask = np.zeros(idx.shape, dtype=np.uint64)
     for k in range(K):
         cpos = gates[h + 1 + k].cpos
-        if hd.csel != 0xFF:
+        if hd.csel != 0xFF and not uniform:
             assert cpos == hd.csel + k, "consecutive-control fan with a gap"
+        if uniform and hd.pad[0]:
+            assert cpos == hd.cpos + k, "consecutive-control uniform fan with a gap"
         mask |= _bit(idx, cpos) << np.uint64(k)
     mask[_bit(idx, hd.tpos) == 0] = 0
     factor = np.ones(idx.shape, dtype=np.complex128)
@@ -116,6 +120,12 @@ def run_plan(passes, n_qubits, fast, state=None):
     idx = np.arange(1 << n_qubits, dtype=np.uint64)
     for p in passes:
         covered = 0
+        # uniform fans (math=fast): listed for the kernel prologue, every control outside the tile
+        tile = set(p.tile_pos[b] for b in range(p.tile_bits))
+        for k in range(p.n_ufans):
+            hd = p.gate[p.ufan_header[k]]
+            assert (hd.flags & GF_FAN_HEADER) and hd.csel == k
+            assert all(p.gate[p.ufan_header[k] + 1 + e].cpos not in tile for e in range(hd.tsel))
         for s in range(p.n_segments):
             seg = p.seg[s]
             assert seg.gate_begin == covered, "segments must tile the gate list"
@@ -125,7 +135,8 @@ def run_plan(passes, n_qubits, fast, state=None):
                 if g.flags & GF_FAN_HEADER:
                     assert gi + g.tsel <= seg.gate_end - 1, "fan crosses its segment"
                     if fast:
-                        _apply_fast_fan(state, idx, p.gate, gi)
+                        uniform = gi in [p.ufan_header[k] for k in range(p.n_ufans)]
+                        _apply_fast_fan(state, idx, p.gate, gi, uniform)
                         gi += 1 + g.tsel
                     else:
                         gi += 1  # exact mode: the entries behind the header are ordinary gate records
