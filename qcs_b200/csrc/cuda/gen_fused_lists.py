@@ -22,8 +22,9 @@ Outputs
 
 Asm operands of QCS<R>_DISPATCH_ASM:  %0 "+r" gate index (advanced past what was executed),
 %1 "l" param-space address of the current DGate, %2 "l" xfull = the thread's basis index with the
-register bits clear (rank bits included), %3 "r" shared-memory address of the uniform-fan factor
-table (math=fast only).
+register bits clear (rank bits included).  The named register `ufb` (declared with the amplitude
+registers, set once per CTA) holds the shared-memory address of the uniform-fan factor table: as
+an asm operand the compiler re-derived it (S2UR + ULEA) in front of every gate.
 """
 import sys
 
@@ -342,7 +343,7 @@ def emit(R, fast=False):
                  "setp.lt.u32 p, kidx, K;", f"@p bra FH{n};", f"bra FM{n};"]
         blocks.append((new_case(sym), body))
     # uniform fan (id 248 + treg + 1, math=fast only; common.h QCS_OP_UFAN_BASE): the product of the
-    # entries' phases is the same for the whole CTA and waits in shared-memory slot `csel` (%3 = base
+    # entries' phases is the same for the whole CTA and waits in shared-memory slot `csel` (ufb = base
     # address of the table).  The exact interpreter never sees one (label kept so that both
     # interpreters share one label table).
     for t in range(-1, R):
@@ -352,7 +353,7 @@ def emit(R, fast=False):
             blocks.append((new_case(sym), ["bra DONE;"]))
             continue
         body = ["bfe.u32 K, w0, 24, 8;", "bfe.u32 c0, w0, 16, 8;", "add.s32 %0, %0, K;",
-                "mad.lo.u32 c0, c0, 16, %3;", "ld.shared.v2.f64 {ar, ai}, [c0];"]
+                "mad.lo.u32 c0, c0, 16, ufb;", "ld.shared.v2.f64 {ar, ai}, [c0];"]
         if t < 0:
             body += [f"ld.param.u8 cs, [%1+{OFF_TPOS}];", "shr.u64 t64, %2, cs;", "and.b64 t64, t64, 1;",
                      "setp.eq.u64 p, t64, 0;", "@p bra DONE;"]
