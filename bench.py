@@ -111,6 +111,16 @@ def _mem_available_gib() -> float:
     return 0.0
 
 
+def _cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def run_reference_sample(n_target: int, budget_s: float = 20.0) -> dict:
     """Times the first gates of the n_target-qubit QFT on the UNMODIFIED reference
     (oracle/_ref), sequential mode on one core and OpenMP mode on all cores."""
@@ -136,7 +146,9 @@ def run_reference_sample(n_target: int, budget_s: float = 20.0) -> dict:
     per_gate_est = 6.0 * 2.0 ** (n - 30)  # s, survey-time single-core figure
     n_gates = max(3, min(24, int(budget_s / max(per_gate_est, 1e-3))))
     out = {}
-    for mode in ("seq", "simd", "omp"):   # the reference's sequential, QCS_SIMD_ONLY and QCS_CPU_OPENMP builds
+    # the reference's sequential, QCS_SIMD_ONLY, QCS_CPU_OPENMP and QCS_MULTI_THREAD (pthread pool,
+    # hard-capped at 4 threads: reference src/qcs.c:38) builds
+    for mode in ("seq", "simd", "omp", "mt"):
         if not po.ref_available(mode):
             continue
         if mode == "omp":
@@ -157,7 +169,8 @@ def run_reference_sample(n_target: int, budget_s: float = 20.0) -> dict:
         dt = time.perf_counter() - t0
         ref.close()
         out[mode] = {"gates": done, "seconds": dt, "gates_per_s_at_sample_width": done / dt,
-                     "gates_per_s": done / dt * scale, "threads": cores if mode == "omp" else 1}
+                     "gates_per_s": done / dt * scale,
+                     "threads": cores if mode == "omp" else 4 if mode == "mt" else 1}
     best = max(out, key=lambda m: out[m]["gates_per_s"])
     return {"value": out[best]["gates_per_s"], "unit": "gates/s",
             "cores": out[best]["threads"], "kind": "reference",
@@ -165,7 +178,7 @@ def run_reference_sample(n_target: int, budget_s: float = 20.0) -> dict:
                        f"qc_h/qc_cphase (oracle/_ref, mode {best}"
                        + (f"; scaled by 2^{n - n_target} to {n_target} qubits" if n != n_target else "")
                        + "), qc_create not timed"),
-            "modes": out, "host_cores": cores}
+            "modes": out, "host_cores": cores, "cpu_model": _cpu_model()}
 
 
 class RefRunner:
@@ -449,7 +462,7 @@ def main() -> None:
     if world == 1 and not args.skip_cpu_baseline:
         try:
             line["cpu_baseline"] = {k: v for k, v in run_reference_sample(n, 20.0).items()
-                                    if k in ("value", "unit", "cores", "kind", "sample", "modes")}
+                                    if k in ("value", "unit", "cores", "kind", "sample", "modes", "host_cores", "cpu_model")}
         except Exception as exc:  # the baseline is a report, never a reason to lose the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "gates/s", "cores": 0, "kind": "reference",
                                     "sample": f"failed: {exc}"}
