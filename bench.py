@@ -224,19 +224,29 @@ def reference_arm(args, rank: int, world: int) -> None:
             n -= 1
         scale = 2.0 ** (n - n_target)
         os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-        runners = {m: RefRunner(n, m) for m in ("seq", "omp") if po.ref_available(m)}
-        probe = {m: r.step(1) for m, r in runners.items()}       # one untimed gate each picks the mode
+        # Which of the reference's CPU modes is fastest on this host is decided on a 26-qubit state
+        # (1 GiB: far beyond the caches, so the per-amplitude cost is the full-width one) -- keeping
+        # four 32 GiB states alive to ask the same question would not fit every box.  Modes:
+        # sequential, QCS_SIMD_ONLY, QCS_CPU_OPENMP (all cores), QCS_MULTI_THREAD (pthread pool, 4
+        # threads: the reference's own cap, src/qcs.c:38).
+        n_probe = min(n, 26)
+        probe = {}
+        for m in ("seq", "simd", "omp", "mt"):
+            if not po.ref_available(m):
+                continue
+            r = RefRunner(n_probe, m)
+            r.step(1)
+            probe[m] = r.step(2) / 2.0 * 2.0 ** (n - n_probe)   # seconds per gate at width n
+            r.close()
         best = min(probe, key=probe.get)
-        for m, r in runners.items():
-            if m != best:
-                r.close()
+        runners = {best: RefRunner(n, best)}
         total_steps = max(1, args.steps + args.warmup)
         g = max(1, int(120.0 / (total_steps * max(probe[best], 1e-3))))   # keep the run near 2 minutes
         g = min(g, 16)
         times = [runners[best].step(g) for _ in range(total_steps)][args.warmup:]
         runners[best].close()
         value = g * len(times) / sum(times) * scale
-        used = 1 if best == "seq" else cores
+        used = {"omp": cores, "mt": min(4, cores)}.get(best, 1)
         kind = "reference"
         modes = {m: {"seconds_per_gate_probe": t} for m, t in probe.items()}
         sample = (f"{g} consecutive gates of the {n}-qubit QFT per step through the reference's own "
