@@ -533,7 +533,7 @@ def light_pass_aux(Circuit, kw, n) -> dict:
     cases = {"one_H_per_pass": ([("h", 8)], {}),
              "H_on_every_qubit": ([("h", q) for q in range(n)], {}),
              "QFT_cut_at_48_flops_per_pass": ([("qft",)], {"pass_flops": 48.0})}
-    from oracle.pyoracle import replay
+    from qcs_b200.workloads import replay
     for name, (script, extra) in cases.items():
         k = dict(kw); k.update(extra)
         c = Circuit(n, **k)
@@ -551,7 +551,7 @@ def light_pass_aux(Circuit, kw, n) -> dict:
 
 def random_circuit_aux(Circuit, kw, world, barrier, dist, torch) -> dict:
     """BASELINE config 5: H/CNOT/RZ brickwork, depth 40, 31+log2(N) qubits (32 GiB shards)."""
-    from oracle.pyoracle import random_circuit_script, replay
+    from qcs_b200.workloads import random_circuit_script, replay
     n = 31 + int(math.log2(world))
     script = random_circuit_script(n, 40)
     c = Circuit(n, **kw)

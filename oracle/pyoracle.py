@@ -385,55 +385,6 @@ class RefLib:
 # Gate scripts: a list of tuples replayable on Oracle / RefLib / product.
 # ---------------------------------------------------------------------------
 
-def replay(backend, script) -> list:
-    """Runs `script` on `backend`; returns the list of values the ops produced
-    (measurement outcomes, shot histograms, argmax, probabilities)."""
-    out = []
-    for op in script:
-        name, args = op[0], op[1:]
-        if name == "srand":
-            srand(args[0])
-        elif name == "measure":
-            out.append(("measure", backend.measure(*args)))
-        elif name == "measure_all":
-            out.append(("measure_all", tuple(backend.measure_all())))
-        elif name == "run_shots":
-            out.append(("run_shots", backend.run_shots(*args)))
-        elif name == "argmax":
-            out.append(("argmax", backend.find_most_likely_state()))
-        elif name == "prob":
-            out.append(("prob", backend.get_probability(*args)))
-        elif name == "grover":
-            backend.grover_search(*args)
-        else:
-            getattr(backend, name)(*args)
-    return out
-
-
-def splitmix64(seed: int):
-    """Deterministic generator shared by every harness."""
-    state = seed & 0xFFFFFFFFFFFFFFFF
-    while True:
-        state = (state + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
-        z = state
-        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
-        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
-        yield z ^ (z >> 31)
-
-
-def random_circuit_script(n: int, depth: int, seed: int = 0x51C50034) -> list:
-    """H/CNOT/RZ brickwork of SURVEY.md section 8(d), config 5."""
-    import math
-    g = splitmix64(seed)
-    script = []
-    for layer in range(depth):
-        for q in range(n):
-            r = next(g)
-            if r & 1:
-                script.append(("h", q))
-            else:
-                theta = 2.0 * math.pi * ((next(g) >> 11) * 2.0 ** -53)
-                script.append(("rz", q, theta))
-        for q in range(layer % 2, n - 1, 2):
-            script.append(("cnot", q, q + 1))
-    return script
+# The scripts and their driver are workload definitions, not oracle arithmetic: they live with the
+# product (qcs_b200/workloads.py) and are re-exported here for the tests.
+from qcs_b200.workloads import random_circuit_script, replay, splitmix64  # noqa: E402,F401

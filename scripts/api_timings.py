@@ -3,7 +3,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from qcs_b200 import Circuit
-from oracle import pyoracle as po
+from qcs_b200 import workloads as po
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 def t(label, f, reps=1):
     t0 = time.perf_counter()

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import torch.distributed as dist
-from oracle import pyoracle as po
+from qcs_b200 import workloads as po
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 shots = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000

@@ -3,7 +3,7 @@ usage: fast_math_sweep.py [qubits] [tile_bits,...] [compute_bound_flops,...]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qcs_b200 import Circuit
-from oracle import pyoracle as po
+from qcs_b200 import workloads as po
 
 PEAK = 6550.1
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")

@@ -1,7 +1,7 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qcs_b200 import Circuit
-from oracle import pyoracle as po
+from qcs_b200 import workloads as po
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 for name, script in (("random_d8", po.random_circuit_script(n, 8)), ("qft", [("qft",)]), ("h_all", [("h", q) for q in range(n)])):
     for fl in (5, 4, 3, 2):

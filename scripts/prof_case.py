@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qcs_b200 import Circuit
-from oracle import pyoracle as po
+from qcs_b200 import workloads as po
 case = sys.argv[1]; n = int(sys.argv[2]); tk = sys.argv[3] if len(sys.argv) > 3 else "tma"
 scripts = {
     "rz_all": [("rz", q, 0.1 * q) for q in range(n)],

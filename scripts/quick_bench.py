@@ -2,7 +2,7 @@
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qcs_b200 import Circuit
-from oracle import pyoracle as po
+from qcs_b200 import workloads as po
 
 def run(n, script, label, **kw):
     c = Circuit(n, semantics="corrected", **kw)

@@ -1,5 +1,5 @@
-"""How far math=fast lands from the bit-exact oracle (development aid): largest component error
-relative to the largest amplitude, on dense states.  usage: fast_math_error.py [qubits ...]"""
+"""How far math=fast lands from the bit-exact oracle (test-side measurement: it runs the CPU oracle as the checker): largest component error
+relative to the largest amplitude, on dense states.  usage: python tests/fast_math_error.py [qubits ...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
