@@ -110,9 +110,9 @@ static int load_options(Options &o) {
   v = option_value("reorder_segments");
   if (!v.empty()) o.reorder_segments = std::atoi(v.c_str());
   if (o.reorder_segments < 1 || o.reorder_segments > QCS_MAX_PASS_SEGMENTS) o.reorder_segments = Options().reorder_segments;
-  if (o.fast_math && (o.sem != SEM_CORRECTED || o.tile_kernel != 3))
+  if (o.fast_math && (o.sem != SEM_CORRECTED || (o.tile_kernel != 3 && o.tile_kernel != 0)))
     return set_error(QCS_CUDA_ERR_INVALID,
-                     "math=fast needs semantics=corrected and tile_kernel=ldg8 (bug-compatible `reference` "
+                     "math=fast needs semantics=corrected and tile_kernel=ldg8|ldg (bug-compatible `reference` "
                      "semantics are bit-exact by definition)");
   return QCS_CUDA_OK;
 }
@@ -273,7 +273,9 @@ static void trace_gates(Engine &e, const std::vector<PhysGate> &gates) {
 
 // smallest tile the selected kernel variant runs on (only ldg8 is instantiated below 12 bits)
 static int min_tile_bits(const Engine &e) {
-  return e.opt.tile_kernel == 3 ? std::min(QCS_MIN_TILE_BITS, e.opt.tile_bits) : QCS_TILE_BITS;
+  if (e.opt.tile_kernel == 3) return std::min(QCS_MIN_TILE_BITS, e.opt.tile_bits);
+  if (e.opt.tile_kernel == 0 && e.opt.fast_math) return 11;  // ldg under math=fast: 11- and 12-bit tiles
+  return QCS_TILE_BITS;
 }
 
 static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysGate> &gates) {

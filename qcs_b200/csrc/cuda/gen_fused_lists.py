@@ -198,7 +198,7 @@ def thread_bit_test(field_shift, pred="p"):
 
 
 def emit(R, fast=False):
-    """fast=False: the bit-exact interpreter.  fast=True (math=fast, R = 3 only): the same case
+    """fast=False: the bit-exact interpreter.  fast=True (math=fast): the same case
     labels and record layout, fused multiply-adds, and controlled-phase fans that multiply the
     entries' phases into ONE per-thread factor (looked up four entries at a time in tables the
     planner lays over the entries' matrix slots) before touching the amplitudes."""
@@ -405,13 +405,14 @@ def main():
         for R in (3, 4):
             out += emit(R)[0]
             out.append("")
-        out += emit(3, fast=True)[0]
-        out.append("")
+        for R in (3, 4):
+            out += emit(R, fast=True)[0]
+            out.append("")
     else:
         out = ["// GENERATED by gen_fused_lists.py -- do not edit.",
                "// symbolic op id (common.h qcs_op_id_*, | QCS_OP_TCTL) -> case label of the generated jump table",
                "#pragma once", ""]
-        assert emit(3, fast=True)[1] == emit(3)[1]  # one label table serves both interpreters
+        assert all(emit(R, fast=True)[1] == emit(R)[1] for R in (3, 4))  # one label table serves both interpreters
         for R in (3, 4):
             table = emit(R)[1]
             out.append(f"static const unsigned short QCS{R}_CASE_LABEL[512] = {{")

@@ -296,6 +296,38 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 #undef QCS_CT
 #undef QCS_NREG_STR
 #undef QCS_LIST
+
+// math=fast with 16 amplitudes per thread (tile_kernel=ldg): what a thread pays per GATE (dispatch,
+// fan walks, table lookups) is spread over twice the amplitudes, and a segment pairs on four
+// positions instead of three.  The bit-exact mode is FP64-bound and gains nothing from this shape;
+// the fast mode is bound by exactly those per-gate costs.
+#define QCS_R 4
+#define QCS_NREG_STR "16"
+#define QCS_LIST(x) QCS4F_##x
+#define QCS_CT (1 << (QCS_T - QCS_R))
+#define QCS_WITH_TMA 0
+
+#define QCS_T 12
+#define QCS_MIN_CTAS 2
+#define QCS_NAME(x) x##_r4f
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+
+#define QCS_T 11
+#define QCS_MIN_CTAS 4
+#define QCS_NAME(x) x##_r4f_t11
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+#undef QCS_WITH_TMA
+
+#undef QCS_R
+#undef QCS_CT
+#undef QCS_NREG_STR
+#undef QCS_LIST
 #undef QCS_WITH_LDG
 #undef QCS_FAST
 
@@ -332,15 +364,16 @@ static int tile_row_bits(const PassParams &p) {
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
                               cudaStream_t stream, int variant, const SwapStore *swap, bool fast) {
   if (swap && variant != 0 && variant != 3) return cudaErrorInvalidValue;  // ldg kernels only
-  if (fast && variant != 3) return cudaErrorInvalidValue;  // math=fast exists for ldg8 only
+  if (fast && variant != 3 && variant != 0) return cudaErrorInvalidValue;  // math=fast: ldg8 and ldg only
   SwapStore sw{};
   if (swap) sw = *swap;
   const int T = params.tile_bits;
   if (T < QCS_MIN_TILE_BITS || T > QCS_TILE_BITS || T > n_local) return cudaErrorInvalidValue;
-  if (T != QCS_TILE_BITS && variant != 3) return cudaErrorInvalidValue;  // only ldg8 has small tiles
+  // only ldg8 has small tiles (and, under math=fast, ldg at 11 bits)
+  if (T != QCS_TILE_BITS && variant != 3 && !(fast && variant == 0 && T == 11)) return cudaErrorInvalidValue;
   const unsigned n_tiles = 1u << (n_local - T);
   static int sm_count = 0;
-  static bool configured[9] = {false, false, false, false, false, false, false, false, false};
+  static bool configured[11] = {false, false, false, false, false, false, false, false, false, false, false};
   if (variant < 0 || variant > 3) return cudaErrorInvalidValue;
   if ((variant >= 2) != (params.reg_bits == 3)) return cudaErrorInvalidValue;
   if (sm_count == 0) {
@@ -355,10 +388,15 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
   // math=fast: the tile + one 16-byte factor per uniform fan behind it
   const size_t smem_ldg = ((size_t)16 << T) + (fast ? 16 * QCS_MAX_PASS_FANS : 0);
   // 3, 4, 5: ldg8 at 12, 11, 10 bits; 6, 7, 8: the same with math=fast
-  const int slot = variant == 3 ? 3 + (QCS_TILE_BITS - T) + (fast ? 3 : 0) : variant;
+  // 9, 10: ldg (16 amplitudes per thread) with math=fast at 12, 11 bits
+  const int slot = variant == 3 ? 3 + (QCS_TILE_BITS - T) + (fast ? 3 : 0)
+                                : (fast && variant == 0) ? 9 + (QCS_TILE_BITS - T) : variant;
   if (!configured[slot]) {
     cudaError_t e;
-    if (fast)
+    if (fast && variant == 0)
+      e = cudaFuncSetAttribute(T == 12 ? fused_pass_ldg_r4f : fused_pass_ldg_r4f_t11,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ldg);
+    else if (fast)
       e = cudaFuncSetAttribute(T == 12 ? fused_pass_ldg_r3f : T == 11 ? fused_pass_ldg_r3f_t11 : fused_pass_ldg_r3f_t10,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ldg);
     else if (variant == 0)
@@ -384,7 +422,12 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
   }
   const unsigned grid = n_tiles < (unsigned)sm_count ? n_tiles : (unsigned)sm_count;
   const uint32_t pf = prefetch_distance(), st = stagger_ns();
-  if (fast) {
+  if (fast && variant == 0) {
+    if (T == 12)
+      fused_pass_ldg_r4f<<<n_tiles, 256, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
+    else
+      fused_pass_ldg_r4f_t11<<<n_tiles, 128, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
+  } else if (fast) {
     if (T == 12)
       fused_pass_ldg_r3f<<<n_tiles, 512, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
     else if (T == 11)

@@ -12,7 +12,8 @@ if os.path.exists(p):
 
 
 def run(n, script, label, reps=3, **kw):
-    c = Circuit(n, semantics="corrected", tile_kernel="ldg8", **kw)
+    kw.setdefault("tile_kernel", "ldg8")
+    c = Circuit(n, semantics="corrected", **kw)
     c.set_timing(True)
     po.replay(c, script); c.flush()
     c.reset_stats()
@@ -48,3 +49,10 @@ for tb in tiles:
         tag = f"fast+reorder/t{tb}/segs{segs}"
         run(n, po.random_circuit_script(n, 8), f"random_d8 {tag}", reps=1, math="fast", tile_bits=tb, reorder_segments=segs)
     run(n, [("qft",)], f"qft fast+reorder/t{tb}", math="fast", tile_bits=tb)
+
+# 16 amplitudes per thread (tile_kernel=ldg) under math=fast: per-gate costs spread over twice the amplitudes
+for tb in (11, 12):
+    run(n, [("qft",)], f"qft fast/ldg16/t{tb}", math="fast", tile_kernel="ldg", tile_bits=tb)
+    run(n, po.random_circuit_script(n, 8), f"random_d8 fast+reorder/ldg16/t{tb}", reps=1, math="fast",
+        tile_kernel="ldg", tile_bits=tb)
+    run(n, [("rz", q, 0.1 * q) for q in range(n)], f"rz_all fast/ldg16/t{tb}", math="fast", tile_kernel="ldg", tile_bits=tb)

@@ -19,7 +19,8 @@ TOL = 1e-12
 
 def Circuit(*a, **k):
     from qcs_b200 import Circuit as C
-    return C(*a, semantics="corrected", tile_kernel="ldg8", math="fast", **k)
+    k.setdefault("tile_kernel", "ldg8")
+    return C(*a, semantics="corrected", math="fast", **k)
 
 
 def _unitary(rng):
@@ -110,6 +111,25 @@ def test_fast_every_target_control_pair(tile_bits):
                 if ctl != t and (ctl + t) % 3 == 0:
                     orc.apply_c1q(m, ctl, t); c.apply_c1q(m, ctl, t)
         _check(c.state(), orc.state(), cls)
+        orc.close(); c.close()
+
+
+@pytest.mark.parametrize("reorder", ["on", "off"])
+@pytest.mark.parametrize("tile_bits", [11, 12])
+@pytest.mark.parametrize("n", [11, 12, 14, 17, 21])
+def test_fast_16_amplitudes_per_thread(n, tile_bits, reorder):
+    """tile_kernel=ldg under math=fast: 16 amplitudes per thread, four pairing positions per segment."""
+    if n < tile_bits:
+        pytest.skip("shard smaller than the tile")
+    rng = np.random.default_rng(7000 + n)
+    init = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    init /= np.linalg.norm(init)
+    for name, script in (("random", _random_script(rng, n, 120)), ("qft", [("qft",)]), ("fans", _fan_script(n, n)),
+                         ("brickwork", po.random_circuit_script(n, 6))):
+        orc = po.Oracle(n, "corrected"); c = Circuit(n, tile_kernel="ldg", tile_bits=tile_bits, reorder=reorder)
+        orc.load_state(init); c.load_state(init)
+        po.replay(orc, script); po.replay(c, script)
+        _check(c.state(), orc.state(), f"{name} n={n}\n{c.describe_plan()[:1500]}")
         orc.close(); c.close()
 
 

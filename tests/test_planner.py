@@ -156,9 +156,9 @@ def _fan_script(n, seed):
 
 
 @pytest.mark.parametrize("math", ["exact", "fast", "fast+reorder"])
-@pytest.mark.parametrize("tile_bits", [10, 11, 12])
+@pytest.mark.parametrize("tile_kernel,tile_bits", [("ldg8", 10), ("ldg8", 11), ("ldg8", 12), ("ldg", 11), ("ldg", 12)])
 @pytest.mark.parametrize("case", ["qft", "random+qft", "fans", "generic"])
-def test_descriptors_compute_the_circuit(case, tile_bits, math):
+def test_descriptors_compute_the_circuit(case, tile_kernel, tile_bits, math):
     from qcs_b200 import Circuit
     from tests import plan_emulator as pe
     n = 13
@@ -183,7 +183,7 @@ def test_descriptors_compute_the_circuit(case, tile_bits, math):
     orc.close()
     reorder = "on" if math.endswith("+reorder") else "off"
     math = math.split("+")[0]
-    c = Circuit(n, dryrun=True, semantics="corrected", tile_kernel="ldg8", tile_bits=tile_bits, math=math,
+    c = Circuit(n, dryrun=True, semantics="corrected", tile_kernel=tile_kernel, tile_bits=tile_bits, math=math,
                 reorder=reorder, peephole="off")
     po.replay(c, script)
     c.flush()
@@ -204,7 +204,8 @@ def test_descriptors_compute_the_circuit(case, tile_bits, math):
 def test_fast_math_needs_corrected_semantics_and_ldg8():
     from qcs_b200 import Circuit
     from qcs_b200.circuit import QcsError
-    for kw in ({"semantics": "reference"}, {"semantics": "corrected", "tile_kernel": "tma"}):
+    for kw in ({"semantics": "reference"}, {"semantics": "corrected", "tile_kernel": "tma"},
+               {"semantics": "corrected", "tile_kernel": "tma16"}):
         with pytest.raises(QcsError):
             Circuit(12, dryrun=True, math="fast", **kw)
     with pytest.raises(QcsError):
