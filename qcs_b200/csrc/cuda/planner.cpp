@@ -614,7 +614,9 @@ Sweep sweep_executable(const std::vector<PhysGate> &g, const std::vector<char> &
 
 std::vector<PassPlan> plan_passes_reordered(const std::vector<PhysGate> &gates, const PlannerConfig &cfg_in) {
   PlannerConfig cfg = cfg_in;
-  cfg.compute_bound_flops = 1e30;  // the tile is chosen here, not by the builder's growth rule
+  // the tile is chosen here, not by the builder's growth rule (stopping heavy passes at 10 bits as the
+  // in-order planner does was measured: QFT unchanged, 31-qubit random circuit 3 % slower)
+  cfg.compute_bound_flops = 1e30;
   const int n_positions = cfg.n_local + cfg.rank_bits;
   const size_t window = 4096;
   std::vector<PassPlan> out;
