@@ -241,7 +241,7 @@ def reference_arm(args, rank: int, world: int) -> None:
         best = min(probe, key=probe.get)
         runners = {best: RefRunner(n, best)}
         total_steps = max(1, args.steps + args.warmup)
-        g = max(1, int(120.0 / (total_steps * max(probe[best], 1e-3))))   # keep the run near 2 minutes
+        g = max(1, int(75.0 / (total_steps * max(probe[best], 1e-3))))   # ~75 s of gates: the whole run (probes, 32 GiB of page faults, steps) stays near 2 minutes
         g = min(g, 16)
         times = [runners[best].step(g) for _ in range(total_steps)][args.warmup:]
         runners[best].close()
