@@ -210,3 +210,42 @@ def test_fast_math_needs_corrected_semantics_and_ldg8():
             Circuit(12, dryrun=True, math="fast", **kw)
     with pytest.raises(QcsError):
         Circuit(12, dryrun=True, semantics="corrected", math="sloppy")
+
+
+def _mixed_script(n, length, seed):
+    """Every gate kind the host layer can queue, on random qubits (all unitary: the comparison is at 1e-12)."""
+    rng = np.random.default_rng(seed)
+    s = []
+    for _ in range(length):
+        q = int(rng.integers(0, n))
+        c = int(rng.integers(0, n - 1)); c = c if c < q else c + 1
+        a = float(rng.uniform(-3, 3))
+        s.append([("h", q), ("x", q), ("y", q), ("z", q), ("phase", q, a), ("rx", q, a), ("ry", q, a), ("rz", q, a),
+                  ("cnot", c, q), ("cphase", c, q, a), ("cphase", c, q, -a), ("rz", q, 0.0)][int(rng.integers(0, 12))])
+    return s
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_reordered_plans_on_random_gate_soup(seed):
+    """Commutation-aware scheduling must never trade two gates that do not commute: random mixtures of
+    pairing, diagonal, controlled and value-preserving gates, 11-14 qubits, every tile size; the plan
+    covers every gate exactly once and computes the oracle's state."""
+    from qcs_b200 import Circuit
+    from tests import plan_emulator as pe
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(11, 15))
+    script = _mixed_script(n, int(rng.integers(40, 400)), seed)
+    tile_kernel, tile_bits = [("ldg8", 10), ("ldg8", 11), ("ldg8", 12), ("ldg", 11)][seed % 4]
+    orc = po.Oracle(n, "corrected")
+    po.replay(orc, script)
+    want = orc.state()
+    orc.close()
+    c = Circuit(n, dryrun=True, semantics="corrected", tile_kernel=tile_kernel, tile_bits=tile_bits, math="fast",
+                peephole="off")
+    po.replay(c, script)
+    c.flush()
+    text, st = c.describe_plan(), c.stats()
+    passes = pe.read_plan(c)
+    c.close()
+    assert sum(p["api"] for p in _parse(text)) == len(script), "every queued gate belongs to exactly one pass"
+    _close(pe.run_plan(passes, n, fast=True), want)
