@@ -583,7 +583,7 @@ Sweep sweep_executable(const std::vector<PhysGate> &g, const std::vector<char> &
   uint8_t state[64] = {0};
   int n_full = 0;
   size_t seen = 0, last_pick = 0;
-  const size_t patience = 4 * (size_t)n_positions + 16;  // gates scanned without a pick before giving up
+  const size_t patience = 16 * (size_t)n_positions + 16;  // gates scanned without a pick before giving up
   for (size_t i = first; i < g.size() && seen < window && n_full < n_positions; i++) {
     if (done[i]) continue;
     if (seen - last_pick > patience) break;
