@@ -104,7 +104,13 @@ int qcs_cuda_write_amplitudes(qcs_cuda_engine *e, int which, long first,
  * "exchange" = p2p|nccl (multi-GPU position swaps: in-place peer-memory kernel, or NCCL send/recv),
  * "tile_bits" = 10|11|12 (largest tile of a fused pass, default 11; a pass runs on the smallest tile that holds its pairing qubits),
  * "peephole" = on|off (corrected semantics: drop exactly self-cancelling X/Y/Z/CNOT/CZ pairs from the queue),
- * "fuse_swaps" = on|off (p2p only: a swap rides on the stores of a fused pass instead of a kernel of its own).
+ * "fuse_swaps" = on|off (p2p only: a swap rides on the stores of a fused pass instead of a kernel of its own),
+ * "math" = exact|fast (default exact: every amplitude bit-identical to the reference's sequential mode.
+ *   fast -- corrected semantics, tile_kernel ldg8|ldg -- trades that for throughput: fused multiply-adds,
+ *   runs of controlled phases merged into one factor, commuting gates scheduled out of order; amplitudes
+ *   then agree with the reference within 1e-12 relative),
+ * "reorder" = on|off, "reorder_segments" = 1..12 (math=fast: commutation-aware scheduling and how many
+ *   segments a reordered pass may spend).
  * Defaults come from QCS_CUDA_<KEY> in the environment; set_default applies
  * to engines created afterwards. */
 int qcs_cuda_set_default(const char *key, const char *value);

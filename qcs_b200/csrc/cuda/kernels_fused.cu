@@ -32,7 +32,11 @@
 //              1 copy warp staging tiles through shared memory with TMA bulk copies
 //   2 "tma"    same, 16 compute warps x 8 amplitudes: twice the warps hide the
 //              per-gate dispatch latency
-//   3 "ldg8"   512 threads x 8 amplitudes, plain loads, 2 CTAs per SM (32 warps per SM)
+//   3 "ldg8"   8 amplitudes per thread, plain loads; 12-, 11- or 10-bit tiles = 2 x 512, 4 x 256 or
+//              8 x 128 threads per SM (32 warps per SM); the default
+// math=fast (opt-in): the same ldg8 / ldg kernel bodies around the QCS<R>F
+// interpreter (fused multiply-adds, fan product tables, per-thread pending factor, uniform-fan
+// prologue): fused_pass_ldg_r3f{,_t11,_t10}, fused_pass_ldg_r4f{,_t11}.
 //
 // Roofline: HBM.  Algorithmic bytes per launch = 32 * 2^nl (every amplitude
 // read once, written once); the planner caps the fused FP64 work per pass so
