@@ -249,3 +249,69 @@ def test_reordered_plans_on_random_gate_soup(seed):
     c.close()
     assert sum(p["api"] for p in _parse(text)) == len(script), "every queued gate belongs to exactly one pass"
     _close(pe.run_plan(passes, n, fast=True), want)
+
+
+# ---- the kernel's own view of a plan: role tables, addresses, case labels (tests/kernel_emulator.py) ---
+@pytest.mark.parametrize("math", ["exact", "fast", "fast+reorder"])
+@pytest.mark.parametrize("tile_kernel,tile_bits", [("ldg8", 10), ("ldg8", 11), ("ldg8", 12), ("ldg", 11), ("ldg", 12),
+                                                    ("tma", 12), ("tma16", 12)])
+@pytest.mark.parametrize("case", ["qft", "random+qft", "fans", "generic"])
+def test_kernel_model_computes_the_circuit(case, tile_kernel, tile_bits, math):
+    """Moves amplitudes through the tile / thread / register roles and decodes case labels exactly as the
+    GPU kernel does (from the same tables): a wrong role table, register index, label, csel or tsel is
+    a wrong amplitude here."""
+    from qcs_b200 import Circuit
+    from tests import kernel_emulator as ke
+    from tests import plan_emulator as pe
+    if math != "exact" and tile_kernel.startswith("tma"):
+        pytest.skip("math=fast exists for the plain-load kernels")
+    n = 13
+    rng = np.random.default_rng(11)
+    if case == "qft":
+        script = [("qft",)]
+    elif case == "random+qft":
+        script = po.random_circuit_script(n, 5, seed=99) + [("qft",)]
+    elif case == "fans":
+        script = _fan_script(n, 5)
+    else:
+        script = _mixed_script(n, 150, 3)
+    init = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    init /= np.linalg.norm(init)
+    orc = po.Oracle(n, "corrected")
+    orc.load_state(init)
+    po.replay(orc, script)
+    want = orc.state()
+    orc.close()
+    reorder = "on" if math.endswith("+reorder") else "off"
+    math = math.split("+")[0]
+    c = Circuit(n, dryrun=True, semantics="corrected", tile_kernel=tile_kernel, tile_bits=tile_bits, math=math,
+                reorder=reorder, peephole="off")
+    po.replay(c, script)
+    c.flush()
+    passes = pe.read_plan(c)
+    c.close()
+    _close(ke.run_plan(passes, n, fast=(math == "fast"), state=init.copy()), want)
+
+
+def test_kernel_model_reference_semantics():
+    """Row-0-only controlled updates (defect D1) through the kernel model: all but the last gate of a flush
+    run fused (the last one alone, after the scratch snapshot), so the state must match the oracle's."""
+    from qcs_b200 import Circuit
+    from tests import kernel_emulator as ke
+    from tests import plan_emulator as pe
+    n = 12
+    rng = np.random.default_rng(5)
+    script = _mixed_script(n, 80, 8)
+    init = rng.normal(size=2 ** n) + 1j * rng.normal(size=2 ** n)
+    orc = po.Oracle(n, "reference")
+    orc.load_state(init)
+    po.replay(orc, script[:-1])
+    want = orc.state()
+    orc.close()
+    c = Circuit(n, dryrun=True, semantics="reference", tile_kernel="ldg8")
+    po.replay(c, script[:-1] + [("rz", 0, 0.0)])   # a value-preserving last gate keeps the fused part = script[:-1]
+    c.flush()
+    passes = pe.read_plan(c)
+    c.close()
+    got = ke.run_plan(passes, n, fast=False, state=init.copy())
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
