@@ -165,6 +165,10 @@ long qcs_cuda_describe_last_plan(qcs_cuda_engine *e, char *buf, long cap);
  * into buf (when cap is large enough); returns the number of passes of the last flush.  Lets a
  * CPU test interpret exactly what the GPU would be handed (tests/test_planner.py). */
 long qcs_cuda_last_plan_raw(qcs_cuda_engine *e, long pass_index, void *buf, long cap);
+/* Sharded engines: returns 1 and the two positions when entry `pass_index` of the last flush trades a
+ * local position for a global one -- on the stores of that pass, or (plan-only engines list these
+ * too, as entries with no segments) as a stand-alone swap between passes; 0 otherwise. */
+long qcs_cuda_last_plan_swap(qcs_cuda_engine *e, long pass_index, int *lpos, int *gpos);
 
 /* Dry-run engines record what a real engine would execute, in order.  Entry i is
  * written as 12 doubles: out[0] = 1 (gate) or 2 (position swap);

@@ -300,7 +300,7 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
 
 // Launches planned passes [first, last); `swap` (may be null) rides on the stores of the last one.
 static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t first, size_t last,
-                         const SwapStore *swap) {
+                         const SwapStore *swap, int swap_lpos = -1, int swap_gpos = -1) {
   if (first >= last) return QCS_CUDA_OK;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   const bool timed = e.timing && !e.opt.dryrun;
@@ -339,6 +339,10 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
     e.pass_bytes += bytes;
     e.pass_flops_per_amp += p.flops_per_amp;
     e.last_plan.push_back(p);
+    if (swap && k + 1 == last) {
+      e.last_plan.back().swap_lpos = swap_lpos;
+      e.last_plan.back().swap_gpos = swap_gpos;
+    }
   }
   if (ev0) {
     cudaEventRecord(ev1, e.stream);
@@ -436,6 +440,15 @@ static void note_swap(Engine &e, int lpos, int gpos) {
 static int swap_positions(Engine &e, int lpos, int gpos) {
   if (!e.opt.dryrun) RC(dist_swap_positions(e, lpos, gpos));
   note_swap(e, lpos, gpos);
+  if (e.opt.dryrun) {  // plan-only engines list stand-alone swaps between the passes (qcs_cuda_last_plan_swap)
+    PassPlan marker;
+    std::memset(&marker.params, 0, sizeof(marker.params));
+    marker.n_gates_api = 0;
+    marker.flops_per_amp = 0.0;
+    marker.swap_lpos = lpos;
+    marker.swap_gpos = gpos;
+    e.last_plan.push_back(marker);
+  }
   return QCS_CUDA_OK;
 }
 
@@ -508,7 +521,7 @@ static int run_range_reordered(Engine &e, const std::vector<HostGate> &q, size_t
       }
     if (e.opt.dryrun) trace_gates(e, ran_gates);
     if (ride) {
-      RC(launch_passes(e, plan, 0, n_run, &sw));
+      RC(launch_passes(e, plan, 0, n_run, &sw, victim, gpos));
       note_swap(e, victim, gpos);
       e.fused_swaps++;
     } else {
@@ -571,7 +584,7 @@ static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, si
       continue;
     }
     if (e.opt.dryrun) trace_gates(e, std::vector<PhysGate>(batch.begin(), batch.begin() + (long)(pass_end - i)));
-    RC(launch_passes(e, plan, 0, chosen + 1, &sw));
+    RC(launch_passes(e, plan, 0, chosen + 1, &sw, victim, gpos));
     note_swap(e, victim, gpos);
     e.fused_swaps++;
     i = pass_end;  // the rest of the batch is planned again under the new layout
@@ -1332,6 +1345,15 @@ long qcs_cuda_describe_last_plan(qcs_cuda_engine *e, char *buf, long cap) {
     buf[n] = 0;
   }
   return (long)s.size() + 1;
+}
+
+long qcs_cuda_last_plan_swap(qcs_cuda_engine *e, long pass_index, int *lpos, int *gpos) {
+  if (!e || pass_index < 0 || pass_index >= (long)e->last_plan.size()) return 0;
+  const PassPlan &p = e->last_plan[(size_t)pass_index];
+  if (p.swap_lpos < 0) return 0;
+  if (lpos) *lpos = p.swap_lpos;
+  if (gpos) *gpos = p.swap_gpos;
+  return 1;
 }
 
 long qcs_cuda_last_plan_raw(qcs_cuda_engine *e, long pass_index, void *buf, long cap) {

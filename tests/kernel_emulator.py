@@ -61,13 +61,63 @@ def _cmul_diag(regs, sel, m_re, m_im):
 
 def run_plan(passes, n_qubits, fast, state=None):
     """Runs the passes the way the kernel would; returns the state vector."""
-    global _INV
-    if _INV is None:
-        _INV = _label_tables()
     if state is None:
         state = np.zeros(1 << n_qubits, dtype=np.complex128)
         state[0] = 1.0
     for p in passes:
+        addr, regs = run_pass(p, state, n_qubits, fast)
+        state = state.copy()
+        state[addr] = regs
+    return state
+
+
+def run_sharded(plans, n_qubits, world, fast, shards=None):
+    """The same for `world` ranks.  plans[rank] = [(PassParams, swap)], swap = None or (lpos, gpos): the
+    pass trades local position lpos for global position gpos on its stores (fused_body.inc OP_STG_SWAP:
+    the element whose bit lpos differs from my rank bit lands in the partner's shard, at the index with
+    bit lpos flipped); an entry with no segments is a stand-alone swap.  Returns the shards."""
+    nl = n_qubits - (world.bit_length() - 1)
+    if shards is None:
+        shards = [np.zeros(1 << nl, dtype=np.complex128) for _ in range(world)]
+        shards[0][0] = 1.0
+    n_entries = len(plans[0])
+    assert all(len(pl) == n_entries for pl in plans), "ranks must execute the same schedule"
+    for k in range(n_entries):
+        swap = plans[0][k][1]
+        assert all(pl[k][1] == swap for pl in plans), "ranks disagree on a swap"
+        outs = []
+        for rank in range(world):
+            p = plans[rank][k][0]
+            if p.n_segments == 0:
+                idx = np.arange(1 << nl, dtype=np.int64)
+                outs.append((idx, shards[rank].copy()))
+            else:
+                assert p.shard_base == rank << nl
+                outs.append(run_pass(p, shards[rank], nl, fast))
+        new = [np.full(1 << nl, np.nan + 0j) for _ in range(world)]
+        for rank in range(world):
+            addr, regs = outs[rank]
+            addr, regs = addr.ravel(), regs.ravel()
+            if swap is None:
+                new[rank][addr] = regs
+                continue
+            lpos, gpos = swap
+            gbit = gpos - nl
+            partner, mybit = rank ^ (1 << gbit), (rank >> gbit) & 1
+            away = ((addr >> lpos) & 1) != mybit
+            new[rank][addr[~away]] = regs[~away]
+            new[partner][addr[away] ^ (1 << lpos)] = regs[away]
+        assert not any(np.isnan(s).any() for s in new), "every amplitude of every shard is written once"
+        shards = new
+    return shards
+
+
+def run_pass(p, state, n_qubits, fast):
+    """One fused pass over a shard of 2^n_qubits amplitudes: returns (store addresses, values)."""
+    global _INV
+    if _INV is None:
+        _INV = _label_tables()
+    if True:
         T, R = p.tile_bits, p.reg_bits
         CT, NREG, n_tiles = 1 << (T - R), 1 << R, 1 << (n_qubits - T)
         inv = _INV[R]
@@ -251,6 +301,4 @@ def run_plan(passes, n_qubits, fast, state=None):
                 regs *= pending[:, :, None]                                # QCS3F_FLUSH_ASM
         addr = addresses(1)
         assert np.array_equal(np.sort(addr.ravel()), np.arange(1 << n_qubits, dtype=np.uint64)), "stores must cover the shard once"
-        state = state.copy()
-        state[addr.astype(np.int64)] = regs
-    return state
+        return addr.astype(np.int64), regs

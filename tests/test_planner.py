@@ -315,3 +315,53 @@ def test_kernel_model_reference_semantics():
     c.close()
     got = ke.run_plan(passes, n, fast=False, state=init.copy())
     assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("mode", ["exact", "fast", "fast-in-order"])
+@pytest.mark.parametrize("case", ["brickwork", "qft", "soup"])
+def test_sharded_kernel_model(case, mode, world):
+    """Every rank's plan run through the kernel model, position swaps on the stores of the passes that
+    carry them (the element whose bit differs from the rank bit lands in the partner's shard at the
+    flipped index): the shards, read under the engine's final layout, are the oracle's state."""
+    import ctypes
+    from qcs_b200 import Circuit, _ffi
+    from tests import kernel_emulator as ke
+    from tests import plan_emulator as pe
+    _, C = _ffi.load()
+    n = 14 if world == 2 else 15
+    script = {"brickwork": po.random_circuit_script(n, 7, seed=21),
+              "qft": [("h", q) for q in range(n)] + [("ry", n - 1, 0.7), ("qft",)],
+              "soup": _mixed_script(n, 160, 17)}[case]
+    kw = {"exact": {}, "fast": {"math": "fast"}, "fast-in-order": {"math": "fast", "reorder": "off"}}[mode]
+    plans, layouts = [], []
+    try:
+        for rank in range(world):
+            C.qcs_cuda_dist_finalize()
+            assert C.qcs_cuda_dist_init_plan_only(rank, world) == 0, _ffi.last_error()
+            c = Circuit(n, dryrun=True, semantics="corrected", tile_kernel="ldg8", peephole="off", **kw)
+            po.replay(c, script)
+            c.flush()
+            entries = []
+            for k, p in enumerate(pe.read_plan(c)):
+                lpos, gpos = ctypes.c_int(-1), ctypes.c_int(-1)
+                has = C.qcs_cuda_last_plan_swap(c.e, k, ctypes.byref(lpos), ctypes.byref(gpos))
+                entries.append((p, (lpos.value, gpos.value) if has else None))
+            plans.append(entries)
+            layouts.append(c.layout())
+            c.close()
+    finally:
+        C.qcs_cuda_dist_finalize()
+    assert all(l == layouts[0] for l in layouts), "ranks disagree on the layout"
+    assert any(sw is not None for _, sw in plans[0]), "the case must exercise a position swap"
+    shards = ke.run_sharded(plans, n, world, fast=(mode != "exact"))
+    phys = np.concatenate(shards)
+    logical = np.arange(1 << n, dtype=np.int64)
+    where = np.zeros_like(logical)
+    for q in range(n):
+        where |= ((logical >> q) & 1) << layouts[0][q]
+    orc = po.Oracle(n, "corrected")
+    po.replay(orc, script)
+    want = orc.state()
+    orc.close()
+    _close(phys[where], want)
