@@ -148,30 +148,38 @@ def run_reference_sample(n_target: int, budget_s: float = 20.0) -> dict:
     out = {}
     # the reference's sequential, QCS_SIMD_ONLY, QCS_CPU_OPENMP and QCS_MULTI_THREAD (pthread pool,
     # hard-capped at 4 threads: reference src/qcs.c:38) builds
-    for mode in ("seq", "simd", "omp", "mt"):
+    # ... and "seqlib": sequential mode built the way the reference's own Makefile builds its library
+    # (one object per source file, c_mul / c_add not inlined) -- reported, ~10x slower than the
+    # single-translation-unit builds above, which are how the reference's README numbers were made
+    for mode in ("seq", "simd", "omp", "mt", "seqlib"):
         if not po.ref_available(mode):
             continue
+        n_gates_mode, n_mode = n_gates, n
+        if mode == "seqlib":  # ~35 s per gate at 30 qubits: sampled on a 26-qubit state (1 GiB, far beyond the caches)
+            n_gates_mode, n_mode = 3, min(n, 26)
         if mode == "omp":
             os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-        ref = po.RefLib(n, mode)
+        ref = po.RefLib(n_mode, mode)
         # warm the pages of both buffers with one untimed gate
-        ref.h(n - 1)
+        ref.h(n_mode - 1)
         done = 0
         t0 = time.perf_counter()
         i, j = 0, 1
         ref.h(0); done += 1
-        while done < n_gates:
+        while done < n_gates_mode:
             ref.cphase(j, i, math.pi / float(1 << (j - i))); done += 1
             j += 1
-            if j >= n:
+            if j >= n_mode:
                 i += 1; j = i + 1
                 ref.h(i); done += 1
         dt = time.perf_counter() - t0
         ref.close()
-        out[mode] = {"gates": done, "seconds": dt, "gates_per_s_at_sample_width": done / dt,
-                     "gates_per_s": done / dt * scale,
-                     "threads": cores if mode == "omp" else 4 if mode == "mt" else 1}
-    best = max(out, key=lambda m: out[m]["gates_per_s"])
+        out[mode] = {"gates": done, "seconds": dt, "sample_qubits": n_mode, "gates_per_s_at_sample_width": done / dt,
+                     "gates_per_s": done / dt * 2.0 ** (n_mode - n_target),
+                     "threads": cores if mode == "omp" else 4 if mode == "mt" else 1,
+                     "build": "multi-TU library (reference Makefile layout)" if mode == "seqlib"
+                              else "single translation unit (the reference's single-header usage)"}
+    best = max((m for m in out if m != "seqlib"), key=lambda m: out[m]["gates_per_s"])
     return {"value": out[best]["gates_per_s"], "unit": "gates/s",
             "cores": out[best]["threads"], "kind": "reference",
             "sample": (f"first {out[best]['gates']} gates of the {n}-qubit QFT through the reference's own "
@@ -239,19 +247,27 @@ def reference_arm(args, rank: int, world: int) -> None:
             probe[m] = r.step(2) / 2.0 * 2.0 ** (n - n_probe)   # seconds per gate at width n
             r.close()
         best = min(probe, key=probe.get)
-        runners = {best: RefRunner(n, best)}
+        # Every step times AT LEAST 8 consecutive gates (an H and the controlled phases behind it).  At
+        # the full width one gate costs ~2 s on this class of host, so 8 gates x (steps + warm-up)
+        # would not end "within a few minutes": the sample is taken on the widest state for which it
+        # does (never below 26 qubits = 1 GiB, far beyond the caches: the per-amplitude cost of a gate
+        # is the full-width one) and scaled by the ratio of the state sizes.
         total_steps = max(1, args.steps + args.warmup)
-        g = max(1, int(75.0 / (total_steps * max(probe[best], 1e-3))))   # ~75 s of gates: the whole run (probes, 32 GiB of page faults, steps) stays near 2 minutes
-        g = min(g, 16)
-        times = [runners[best].step(g) for _ in range(total_steps)][args.warmup:]
-        runners[best].close()
+        g = 8
+        n_run = n
+        while n_run > 26 and g * total_steps * probe[best] * 2.0 ** (n_run - n) > 100.0:
+            n_run -= 1
+        scale = 2.0 ** (n_run - n_target)
+        runner = RefRunner(n_run, best)
+        times = [runner.step(g) for _ in range(total_steps)][args.warmup:]
+        runner.close()
         value = g * len(times) / sum(times) * scale
         used = {"omp": cores, "mt": min(4, cores)}.get(best, 1)
         kind = "reference"
         modes = {m: {"seconds_per_gate_probe": t} for m, t in probe.items()}
-        sample = (f"{g} consecutive gates of the {n}-qubit QFT per step through the reference's own "
+        sample = (f"{g} consecutive gates of the {n_run}-qubit QFT per step through the reference's own "
                   f"qc_h/qc_cphase (oracle/_ref mode {best}, {used} thread(s) of {cores} cores"
-                  + (f"; scaled by 2^{n - n_target} to {n_target} qubits" if n != n_target else "")
+                  + (f"; scaled by 2^{n_run - n_target} to {n_target} qubits" if n_run != n_target else "")
                   + "); qc_create not timed")
     # same unit as our arm: gates x 2^30-amplitude shards per second (at N = 1 plain gates/s of the
     # 30-qubit QFT; at N > 1 the reference sweeps N shards' worth of amplitudes per gate)
@@ -272,6 +288,109 @@ def reference_arm(args, rank: int, world: int) -> None:
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
+# ----------------------------------------------------------------------------- sharded parity
+# The driver's GPU test box has one GPU, so tests/test_dist_gpu.py is skipped there.  A multi-rank
+# bench run therefore repeats a parity check in front of its timed region: the sharded engine against
+# (a) the committed golden vectors of the real reference (tests/golden/golden_v1.npz; bit for bit,
+# both semantics) and (b) this rank's own single-GPU engine on 26-qubit circuits (QFT, brickwork),
+# bit for bit in the default mode and within 1e-12 under math=fast.  The verdict is part of the JSON
+# line (sanity.sharded_parity).  Nothing here touches oracle/.
+PARITY_QUBITS = 26
+
+
+def _parity_scripts(n):
+    from qcs_b200.workloads import random_circuit_script
+    return {"qft": [("x", 1), ("ry", n - 1, 0.3), ("h", n - 2), ("qft",)],
+            "brickwork_d10": random_circuit_script(n, 10, seed=5)}
+
+
+def sharded_parity_reference(Circuit, rank: int, world: int) -> dict:
+    """BEFORE the communicator exists: this rank's slice of the single-GPU engine's result."""
+    from qcs_b200.workloads import replay
+    n = PARITY_QUBITS
+    count = (1 << n) // world
+    out = {}
+    for name, script in _parity_scripts(n).items():
+        c = Circuit(n, semantics="corrected")
+        replay(c, script)
+        full = c.state()
+        out[name] = (full[rank * count:(rank + 1) * count].copy(), float(abs(full).max()))
+        c.close()
+    return out
+
+
+def sharded_parity_check(Circuit, want: dict, rank: int, world: int, dist, torch) -> dict:
+    import numpy as np
+    from qcs_b200.workloads import replay
+    from tests.golden.cases import CASES
+    n = PARITY_QUBITS
+    rank_bits = int(math.log2(world))
+    res = {"qubits": n, "exact_mismatches": 0, "fast_max_rel_err": 0.0, "golden_cases": 0, "golden_mismatches": 0,
+           "remaps": 0, "fused_remaps": 0}
+    for name, script in _parity_scripts(n).items():
+        shard, scale = want[name]
+        for mode in ("exact", "fast"):
+            c = Circuit(n, semantics="corrected", math=mode)
+            replay(c, script); c.flush()
+            st = c.stats()
+            got = c.state()
+            if mode == "exact":
+                res["exact_mismatches"] += int(np.sum(got != shard))
+                res["remaps"] += st["remaps"]; res["fused_remaps"] += st["fused_remaps"]
+            else:
+                res["fast_max_rel_err"] = max(res["fast_max_rel_err"], float(np.abs(got - shard).max() / scale))
+            c.close()
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+    for name in sorted(CASES):
+        nq, script = CASES[name]
+        if nq - rank_bits < 2:
+            continue
+        count = (1 << nq) // world
+        for sem in ("reference", "corrected"):
+            c = Circuit(nq, semantics=sem)
+            vals = replay(c, script)
+            key = f"{name}/{sem}"
+            bad = int(np.sum(c.state() != golden[key + "/state"][rank * count:(rank + 1) * count]))
+            for k, (kind, v) in enumerate(vals):
+                bad += int(not np.array_equal(np.asarray(v), golden[f"{key}/out{k}_{kind}"]))
+            res["golden_cases"] += 1
+            res["golden_mismatches"] += bad
+            c.close()
+    t = torch.tensor([res["exact_mismatches"], res["golden_mismatches"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    e = torch.tensor([res["fast_max_rel_err"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    res["exact_mismatches"], res["golden_mismatches"] = int(t[0]), int(t[1])
+    res["fast_max_rel_err"] = float(e[0])
+    res["ok"] = res["exact_mismatches"] == 0 and res["golden_mismatches"] == 0 and res["fast_max_rel_err"] <= 1e-12
+    res["what"] = (f"sharded engine on {world} ranks vs each rank's own single-GPU run of a {n}-qubit QFT and a depth-10 "
+                   "brickwork circuit (== in the default mode, 1e-12 under math=fast) and vs the committed golden "
+                   "vectors of the real reference (==, both semantics)")
+    return res
+
+
+def ncu_traffic(n_local: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the heaviest fused pass, read from the
+    committed `ncu --set full` summary of this workload (profiles/, scripts/ncu_summary.py)."""
+    import csv
+    for name in ("r2_qft30_exact_summary.csv", "r1u_qft30_exact_summary.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        if n_local != 30 or not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        try:
+            ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "byte": 1.0}.get(rows[1][ir], 1e9)
+            launches = [r for r in rows[2:] if "fused_pass" in r[0]]
+            heavy = max(launches, key=lambda r: float(r[it]))
+            return {"bytes_per_launch": (float(heavy[ir]) + float(heavy[iw])) * unit, "source": f"profiles/{name}",
+                    "launch": "heaviest fused pass of the capture"}
+        except (ValueError, IndexError):
+            continue
+    return None
+
+
 # ----------------------------------------------------------------------------- our arm
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -284,6 +403,7 @@ def main() -> None:
     ap.add_argument("--pass-flops", type=float, default=None)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-aux", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true", help="N > 1: skip the sharded parity check in front of the timed region")
     ap.add_argument("--aux", action="store_true", help="also run the random-circuit config at N=1 (31 qubits)")
     args = ap.parse_args()
 
@@ -308,6 +428,7 @@ def main() -> None:
     from qcs_b200 import Circuit, _ffi
     H, C = _ffi.load()
 
+    parity_want = sharded_parity_reference(Circuit, rank, world) if world > 1 and not args.skip_parity else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world,
@@ -325,6 +446,11 @@ def main() -> None:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    parity = None
+    if parity_want is not None:
+        parity = sharded_parity_check(Circuit, parity_want, rank, world, dist, torch)
+        parity_want = None
 
     n = args.qubits or (30 + int(math.log2(world)))
     gates = qft_gate_count(n)
@@ -356,6 +482,7 @@ def main() -> None:
     clocks = sampler.stop() if rank == 0 else None
     st = c.stats()
     plan_text = c.describe_plan()
+    passes_last_step = c.pass_info()   # the last timed step, pass by pass
     if world > 1:
         t = torch.tensor([dev_s, wall_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -368,7 +495,7 @@ def main() -> None:
     c.close()
 
     # ---------------- end to end through the public C API (`e2e`) -----------------------------
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, args.steps)
     barrier()
     t0 = time.perf_counter()
     d2h = 0
@@ -391,8 +518,12 @@ def main() -> None:
     h2d_per_step = int(passes_per_step * C.qcs_cuda_pass_descriptor_bytes())
 
     aux = None
-    if (world > 1 or args.aux) and not args.skip_aux:
+    strong = None
+    if not args.skip_aux:
+        # BASELINE config 5 (and its 1-GPU baseline at N = 1: the number the 8-GPU efficiency is divided by)
         aux = random_circuit_aux(Circuit, kw, world, barrier, dist, torch)
+        if world > 1:
+            strong = strong_scaling_aux(Circuit, kw, world, barrier, dist, torch, args.steps, warmup)
     light = None
     fast = None
     if world == 1 and not args.skip_aux:
@@ -402,6 +533,8 @@ def main() -> None:
             fast = fast_math_aux(Circuit, kw, n, args.steps, warmup, world, barrier, dist, torch)
             if aux is not None:
                 kf = dict(kw); kf["math"] = "fast"
+                if strong is not None:
+                    strong["math_fast"] = strong_scaling_aux(Circuit, kf, world, barrier, dist, torch, args.steps, warmup)
                 fast["random_circuit"] = random_circuit_aux(Circuit, kf, world, barrier, dist, torch)
         except Exception as exc:
             fast = {"failed": repr(exc)}
@@ -430,6 +563,22 @@ def main() -> None:
                 "frac": ops / (st["pass_ms"] * 1e-3) / fp64_peak.value,
                 "ops_per_amplitude_per_step": st["pass_flops_per_amp"] / args.steps,
                 "peak_source": "measured in this run (qcs_cuda_probe_fp64: mul.rn/add.rn chains, no memory traffic)"}
+    # Pass by pass (last timed step): a pass costs max(memory time, FP64 issue time), so each pass is held
+    # against BOTH ceilings and scored by the larger fraction -- cutting a circuit into more, lighter
+    # passes raises the HBM fraction of every pass without making anything faster, this figure does not move.
+    per_pass = []
+    for k, pi in enumerate(passes_last_step):
+        if pi["ms"] <= 0:
+            continue
+        hbm_frac = 32.0 * 2.0 ** n_local / (pi["ms"] * 1e-3) / 1e9 / peak
+        fp64_frac = (pi["flops_per_amp"] * 2.0 ** n_local / (pi["ms"] * 1e-3) / fp64_peak.value) if fp64_peak.value > 0 else None
+        per_pass.append({"pass": k, "ms": pi["ms"], "tile_bits": pi["tile_bits"], "segments": pi["segments"],
+                         "fp64_ops_per_amplitude": pi["flops_per_amp"], "hbm_frac": hbm_frac, "fp64_frac": fp64_frac,
+                         "bound": "fp64" if (fp64_frac or 0) > hbm_frac else "hbm",
+                         "frac_of_binding_ceiling": max(hbm_frac, fp64_frac or 0.0)})
+    tot_ms = sum(q["ms"] for q in per_pass)
+    binding = (sum(q["frac_of_binding_ceiling"] * q["ms"] for q in per_pass) / tot_ms) if tot_ms > 0 else None
+    traffic = ncu_traffic(n_local)
     line = {
         "metric": "gates/s", "value": value, "unit": "gates/s", "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * dev_s / args.steps,
@@ -455,9 +604,12 @@ def main() -> None:
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": 32.0 * 2 ** n_local,
             "avg_launch_ms": st["pass_ms"] / st["passes"] if st["passes"] else None,
-            "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(n_local),
+            "traffic": traffic["bytes_per_launch"] if traffic else None,
+            "traffic_source": traffic,
             "share_of_step": (st["pass_ms"] * 1e-3) / dev_s if dev_s > 0 else None,
             "co_limiter_fp64": fp64,
+            "per_pass": per_pass,
+            "time_weighted_frac_of_binding_ceiling": binding,
         },
         "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": h2d_per_step,
                 "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps,
@@ -465,8 +617,10 @@ def main() -> None:
                         "qc_find_most_likely_state + qc_destroy through libqcs.so"},
         "gpu_launches": st["kernel_launches"],
         "clocks": clocks,
-        "sanity": {"p(|0>) after the timed QFTs": p0},
+        "sanity": {"p(|0>) after the timed QFTs": p0, "sharded_parity": parity},
     }
+    if strong:
+        line["aux_strong_scaling_qft30"] = strong
     if aux:
         line["aux_random_circuit"] = aux
     if light:
@@ -484,11 +638,6 @@ def main() -> None:
     if world > 1:
         C.qcs_cuda_dist_finalize()
         dist.destroy_process_group()
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum per fused-pass launch, from the ncu --set full
-# captures committed under profiles/ (keyed by local qubits); None where not captured.
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {28: 8.53e9, 30: 34.30e9}  # profiles/r1g_qft30_ldg8_summary.csv
 
 
 def fast_math_aux(Circuit, kw, n, steps, warmup, world, barrier, dist, torch) -> dict:
@@ -525,6 +674,32 @@ def fast_math_aux(Circuit, kw, n, steps, warmup, world, barrier, dist, torch) ->
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "avg_launch_ms": st["pass_ms"] / st["passes"]},
             "fp64_instructions_per_amplitude_per_step": st["pass_flops_per_amp"] / steps}
+
+
+def strong_scaling_aux(Circuit, kw, world, barrier, dist, torch, steps, warmup) -> dict:
+    """the 30-qubit QFT (fixed total work) sharded over the N GPUs of this run."""
+    n = 30
+    c = Circuit(n, **kw)
+    c.set_timing(True)
+    for _ in range(warmup):
+        c.qft(); c.flush()
+    barrier()
+    c.reset_stats()
+    c.marker(0)
+    for _ in range(steps):
+        c.qft(); c.flush()
+    c.marker(1)
+    barrier()
+    dev_s = c.marker_elapsed_ms(0, 1) * 1e-3
+    st = c.stats()
+    c.close()
+    t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s = float(t[0])
+    return {"workload": f"30-qubit QFT on {world} GPUs ({16 // world} GiB per GPU), strong scaling",
+            "gates_per_s": qft_gate_count(n) * steps / dev_s, "ms_per_step": 1e3 * dev_s / steps,
+            "passes_per_step": st["passes"] / steps, "remaps_per_step": st["remaps"] / steps,
+            "fused_remap_pass_ms": (st["fused_remap_pass_ms"] / st["fused_remaps"]) if st["fused_remaps"] else None}
 
 
 def light_pass_aux(Circuit, kw, n) -> dict:

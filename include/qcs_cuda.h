@@ -114,6 +114,12 @@ int qcs_cuda_write_amplitudes(qcs_cuda_engine *e, int which, long first,
  * Defaults come from QCS_CUDA_<KEY> in the environment; set_default applies
  * to engines created afterwards. */
 int qcs_cuda_set_default(const char *key, const char *value);
+/* The process-wide default for `key` set by qcs_cuda_set_default: copies it into buf (when cap allows)
+ * and returns its length, or -1 when no default is set (the environment / built-in value applies). */
+long qcs_cuda_get_default(const char *key, char *buf, long cap);
+/* Freed state buffers are kept for the next qc_create of the same size (cudaMalloc / cudaFree of a
+ * 16 GiB state cost 10-350 ms); this returns them to the driver.  Returns the bytes released. */
+long qcs_cuda_trim_pool(void);
 int qcs_cuda_num_qubits(const qcs_cuda_engine *e);
 /* Current layout: perm[q] = physical index position of logical qubit q (identity on one GPU;
  * position swaps change it when the state is sharded).  perm must hold n_qubits ints. */
@@ -169,6 +175,11 @@ long qcs_cuda_last_plan_raw(qcs_cuda_engine *e, long pass_index, void *buf, long
  * local position for a global one -- on the stores of that pass, or (plan-only engines list these
  * too, as entries with no segments) as a stand-alone swap between passes; 0 otherwise. */
 long qcs_cuda_last_plan_swap(qcs_cuda_engine *e, long pass_index, int *lpos, int *gpos);
+/* Per-pass figures of the last flush (timing enabled): device time in ms (-1 when not measured), the
+ * planner's FP64 operation count per amplitude, tile bits and segment count of pass `pass_index`.
+ * Any out pointer may be NULL.  Returns the number of passes of the last flush. */
+long qcs_cuda_last_plan_pass_info(qcs_cuda_engine *e, long pass_index, double *ms, double *flops_per_amp,
+                                  int *tile_bits, int *segments);
 
 /* Dry-run engines record what a real engine would execute, in order.  Entry i is
  * written as 12 doubles: out[0] = 1 (gate) or 2 (position swap);

@@ -16,12 +16,19 @@
  * Compiled with -std=c89 like the reference Makefile:8, which also turns FMA
  * contraction off (ISO mode) -- the canonical oracle arithmetic.
  */
+#ifndef QCS_REF_MULTI_TU
 #include "complex.c"
 #include "q_matrix.c"
 #include "q_state.c"
 #include "q_utils.c"
 #include "q_gates.c"
 #include "thread_pools.c"
+#endif
+/* QCS_REF_MULTI_TU (oracle/Makefile, libqcsref_seqlib.so): the layout of the reference's own
+ * Makefile instead -- one object per source file, so c_mul / c_add (src/complex.c) are CALLS from
+ * the gate loops of src/q_gates.c, not inlined.  Only qcs.c is included here (the accessors below
+ * need its private struct t_q_circuit); the other files are compiled on their own and linked in.
+ * A CPU baseline only (~20x slower than the single-header build). */
 #include "qcs.c"
 
 /* qc_cphase is exported by the reference (src/qcs.c:431) but not declared in

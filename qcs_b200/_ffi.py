@@ -56,6 +56,8 @@ CUDA_ABI = {
     "qcs_cuda_read_amplitudes": (_I, [_P, _I, _L, _L, _DP]),
     "qcs_cuda_write_amplitudes": (_I, [_P, _I, _L, _L, _DP]),
     "qcs_cuda_set_default": (_I, [ctypes.c_char_p, ctypes.c_char_p]),
+    "qcs_cuda_get_default": (_L, [ctypes.c_char_p, ctypes.c_char_p, _L]),
+    "qcs_cuda_trim_pool": (_L, []),
     "qcs_cuda_num_qubits": (_I, [_P]),
     "qcs_cuda_get_layout": (_I, [_P, _IP]),
     "qcs_cuda_get_stats": (_I, [_P, ctypes.POINTER(Stats)]),
@@ -68,6 +70,7 @@ CUDA_ABI = {
     "qcs_cuda_describe_last_plan": (_L, [_P, ctypes.c_char_p, _L]),
     "qcs_cuda_last_plan_raw": (_L, [_P, _L, ctypes.c_void_p, _L]),
     "qcs_cuda_last_plan_swap": (_L, [_P, _L, _IP, _IP]),
+    "qcs_cuda_last_plan_pass_info": (_L, [_P, _L, _DP, _DP, _IP, _IP]),
     "qcs_cuda_last_error": (ctypes.c_char_p, []),
     "qcs_cuda_dist_unique_id": (_I, [ctypes.c_char_p]),
     "qcs_cuda_dist_init": (_I, [_I, _I, ctypes.c_char_p, _I]),

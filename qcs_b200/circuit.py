@@ -26,6 +26,14 @@ def set_default(key: str, value: str | None) -> None:
     cuda.qcs_cuda_set_default(key.encode(), None if value is None else str(value).encode())
 
 
+def get_default(key: str) -> str | None:
+    """The process-wide default set by set_default(), or None."""
+    _, cuda = _ffi.load()
+    buf = ctypes.create_string_buffer(256)
+    n = cuda.qcs_cuda_get_default(key.encode(), buf, 256)
+    return None if n < 0 else buf.value.decode()
+
+
 class Circuit:
     def __init__(self, num_qubits: int, *, semantics: str | None = None,
                  fusion: str | None = None, dryrun: bool | None = None,
@@ -40,15 +48,17 @@ class Circuit:
                 "tile_bits": None if tile_bits is None else str(int(tile_bits)),
                 "dryrun": None if dryrun is None else ("1" if dryrun else "0"),
                 "pass_flops": None if pass_flops is None else repr(float(pass_flops))}
+        # per-circuit options travel as process-wide defaults around qc_create (the C API has no
+        # configuration object); whatever defaults the caller had set before are put back afterwards
+        saved = {k: get_default(k) for k, v in opts.items() if v is not None}
         for k, v in opts.items():
             if v is not None:
                 set_default(k, v)
         try:
             self.c = self.H.qc_create(num_qubits)
         finally:
-            for k, v in opts.items():
-                if v is not None:
-                    set_default(k, None)
+            for k, v in saved.items():
+                set_default(k, v)
         if not self.c:
             raise QcsError(f"qc_create({num_qubits}) failed: {_ffi.last_error()}")
         self.e = self.H.qc_cuda_engine(self.c)
@@ -226,6 +236,20 @@ class Circuit:
                 kf = int(buf[1])
                 out.append(("gate", kf & 0xff, kf >> 8, int(buf[2]), int(buf[3]), [buf[4 + k] for k in range(8)]))
         return out
+
+    def pass_info(self) -> list:
+        """Passes of the last flush: dicts with ms (device time, timing on), flops_per_amp, tile_bits, segments."""
+        out = []
+        n = self.C.qcs_cuda_last_plan_pass_info(self.e, -1, None, None, None, None)
+        for k in range(n):
+            ms, fl = ctypes.c_double(), ctypes.c_double()
+            tb, sg = ctypes.c_int(), ctypes.c_int()
+            self.C.qcs_cuda_last_plan_pass_info(self.e, k, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(tb), ctypes.byref(sg))
+            out.append({"ms": ms.value, "flops_per_amp": fl.value, "tile_bits": tb.value, "segments": sg.value})
+        return out
+
+    def pass_times(self) -> list:
+        return [p["ms"] for p in self.pass_info()]
 
     def describe_plan(self) -> str:
         need = self.C.qcs_cuda_describe_last_plan(self.e, None, 0)

@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only: the library itself is dlopen'ed
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -140,8 +141,12 @@ int dist_open_peers(Engine &e) {
   if (!d.active || e.opt.dryrun) return QCS_CUDA_OK;
   const size_t n_tiles = e.nl >= QCS_MIN_TILE_BITS ? (size_t)1 << (e.nl - QCS_MIN_TILE_BITS) : 0;
   if (n_tiles) {
-    CK(cudaMalloc(&e.tile_flags, n_tiles * sizeof(uint32_t)));
-    CK(cudaMemset(e.tile_flags, 0, n_tiles * sizeof(uint32_t)));
+    // one word per tile + (behind them) the abort word of the bounded handshake wait
+    CK(cudaMalloc(&e.tile_flags, (n_tiles + 1) * sizeof(uint32_t)));
+    CK(cudaMemset(e.tile_flags, 0, (n_tiles + 1) * sizeof(uint32_t)));
+    e.swap_abort_flag = e.tile_flags + n_tiles;
+    if (!e.swap_status_host) CK(cudaMallocHost(&e.swap_status_host, sizeof(int)));
+    *e.swap_status_host = 0;
   }
   struct Handles { cudaIpcMemHandle_t live, flags; } mine;
   std::memset(&mine, 0, sizeof(mine));
@@ -184,6 +189,9 @@ void dist_close_peers(Engine &e) {
   e.peer_flags.clear();
   if (e.tile_flags) cudaFree(e.tile_flags);
   e.tile_flags = nullptr;
+  e.swap_abort_flag = nullptr;
+  if (e.swap_status_host) cudaFreeHost(e.swap_status_host);
+  e.swap_status_host = nullptr;
 }
 
 static int stream_barrier(Engine &e, cudaStream_t stream) {
@@ -193,6 +201,22 @@ static int stream_barrier(Engine &e, cudaStream_t stream) {
   NK(ncclAllReduce(flag, flag, 1, ncclInt, ncclSum, (ncclComm_t)d.comm, stream));
   (void)e;
   return QCS_CUDA_OK;
+}
+
+// How long a CTA of a swap-carrying pass waits for its partner CTA (QCS_CUDA_SWAP_TIMEOUT_MS, default
+// 20 s: the ranks enter a pass up to a whole pass apart, but never seconds).
+static unsigned long long swap_spin_limit() {
+  static unsigned long long ticks = 0;
+  if (!ticks) {
+    const char *v = getenv("QCS_CUDA_SWAP_TIMEOUT_MS");
+    double ms = v ? atof(v) : 20000.0;
+    if (!(ms > 0)) ms = 20000.0;
+    int dev = 0, khz = 1965000;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    ticks = (unsigned long long)(ms * (double)khz);
+  }
+  return ticks;
 }
 
 bool dist_p2p_available(const Engine &e) {
@@ -214,12 +238,39 @@ bool dist_fused_swap_args(Engine &e, int lpos, int gpos, SwapStore &sw) {
   sw.lpos = (uint32_t)lpos;
   sw.my_gbit = (uint32_t)((d.rank >> gbit) & 1);
   sw.lpos_in_tile = 0;  // the caller knows the pass's tile
+  sw.abort_flag = e.swap_abort_flag;
+  sw.spin_limit = swap_spin_limit();
   return true;
 }
 
 // After a pass that stored into the partner's shard: nobody reads swapped data before both
-// ranks' kernels (hence their remote stores) have completed.
-int dist_after_fused_swap(Engine &e) { return stream_barrier(e, e.stream); }
+// ranks' kernels (hence their remote stores) have completed.  The same 4-byte all-reduce carries the
+// abort words of the bounded handshake wait: its sum lands in pinned host memory and is looked at
+// at the next host synchronisation (dist_check_fused_swaps) -- non-zero on EVERY rank when any CTA
+// on any rank gave up waiting for its partner.
+int dist_after_fused_swap(Engine &e) {
+  DistContext &d = dist();
+  int *flag = (int *)((char *)g_small_dev + kSmallBytes - 64);  // clear of dist_allgather_host's area
+  CK(cudaMemcpyAsync(flag, e.swap_abort_flag, sizeof(int), cudaMemcpyDeviceToDevice, e.stream));
+  NK(ncclAllReduce(flag, flag, 1, ncclInt, ncclSum, (ncclComm_t)d.comm, e.stream));
+  CK(cudaMemcpyAsync(e.swap_status_host, flag, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+  e.swap_status_pending = true;
+  return QCS_CUDA_OK;
+}
+
+// Call after the stream has been synchronised.
+int dist_check_fused_swaps(Engine &e) {
+  if (!e.swap_status_pending) return QCS_CUDA_OK;
+  e.swap_status_pending = false;
+  if (e.swap_status_host && *e.swap_status_host != 0) {
+    e.poisoned = true;
+    return set_error(QCS_CUDA_ERR_CUDA,
+                     "position swap: %d rank(s) gave up waiting for the partner's tiles (partner kernel not "
+                     "running: failed launch, diverged plan or a co-tenant on the GPU); the state is invalid",
+                     *e.swap_status_host);
+  }
+  return QCS_CUDA_OK;
+}
 
 // In-place position swap on `stream`.
 int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos) {
@@ -237,7 +288,7 @@ int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos) {
   }
   int rc = stream_barrier(e, stream);  // the partner finished its previous work on these elements
   if (rc) return rc;
-  p2p_swap_kernel<<<148 * 16, 256, 0, stream>>>(e.live, e.peer_live[partner], begin, end, lpos,
+  p2p_swap_kernel<<<(unsigned)device_sm_count() * 16, 256, 0, stream>>>(e.live, e.peer_live[partner], begin, end, lpos,
                                                 1ull - mybit);
   CK(cudaGetLastError());
   e.kernel_launches++;
@@ -276,7 +327,7 @@ int dist_swap_positions(Engine &e, int lpos, int gpos) {
   if (contiguous) {
     src = e.live + leaving * n_half;  // the leaving half is one contiguous range
   } else {
-    pack_half_kernel<<<148 * 8, 256, 0, e.stream>>>(e.live, send_buf, n_half, lpos, leaving);
+    pack_half_kernel<<<(unsigned)device_sm_count() * 8, 256, 0, e.stream>>>(e.live, send_buf, n_half, lpos, leaving);
     CK(cudaGetLastError());
     e.kernel_launches++;
   }
@@ -288,7 +339,7 @@ int dist_swap_positions(Engine &e, int lpos, int gpos) {
     CK(cudaMemcpyAsync(e.live + leaving * n_half, recv_buf, half_bytes, cudaMemcpyDeviceToDevice,
                        e.stream));
   } else {
-    unpack_half_kernel<<<148 * 8, 256, 0, e.stream>>>(e.live, recv_buf, n_half, lpos, leaving);
+    unpack_half_kernel<<<(unsigned)device_sm_count() * 8, 256, 0, e.stream>>>(e.live, recv_buf, n_half, lpos, leaving);
     CK(cudaGetLastError());
     e.kernel_launches++;
   }

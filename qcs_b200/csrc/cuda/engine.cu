@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 
 #include "../../../include/qcs_cuda.h"
@@ -50,10 +51,19 @@ static std::map<std::string, std::string> &defaults() {
   static std::map<std::string, std::string> d;
   return d;
 }
+// engines may be created from several host threads (one circuit per thread): the option table and
+// the buffer pool are the process-wide state they share
+static std::mutex &globals_mutex() {
+  static std::mutex m;
+  return m;
+}
 
 static std::string option_value(const char *key) {
-  auto it = defaults().find(key);
-  if (it != defaults().end()) return it->second;
+  {
+    std::lock_guard<std::mutex> lock(globals_mutex());
+    auto it = defaults().find(key);
+    if (it != defaults().end()) return it->second;
+  }
   std::string env = "QCS_CUDA_";
   for (const char *p = key; *p; p++) env += (char)toupper(*p);
   const char *v = std::getenv(env.c_str());
@@ -135,11 +145,12 @@ bool pool_enabled() {
   }
   return on == 1;
 }
-void pool_trim() {
+void pool_trim_locked() {
   for (auto &p : g_pool) cudaFree(p.ptr);
   g_pool.clear();
 }
 cudaError_t pool_alloc(void **out, size_t bytes) {
+  std::lock_guard<std::mutex> lock(globals_mutex());
   int dev = 0;
   cudaGetDevice(&dev);
   for (size_t i = 0; i < g_pool.size(); i++) {
@@ -152,7 +163,7 @@ cudaError_t pool_alloc(void **out, size_t bytes) {
   cudaError_t e = cudaMalloc(out, bytes);
   if (e == cudaErrorMemoryAllocation && !g_pool.empty()) {
     cudaGetLastError();
-    pool_trim();
+    pool_trim_locked();
     e = cudaMalloc(out, bytes);
   }
   return e;
@@ -169,6 +180,7 @@ void pool_free(void *ptr, size_t bytes) {
     cudaFree(ptr);
     return;
   }
+  std::lock_guard<std::mutex> lock(globals_mutex());
   g_pool.push_back(PoolEntry{ptr, bytes, dev});
   size_t total = 0;
   for (auto &p : g_pool) total += p.bytes;
@@ -193,13 +205,20 @@ static cudaEvent_t get_event(Engine &e) {
 }
 
 static void fold_events(Engine &e) {
-  if (e.pending_pass_events.empty() && e.pending_xchg_events.empty() && e.pending_fused_events.empty()) return;
+  if (e.pending_pass_events.empty() && e.pending_xchg_events.empty()) return;
   cudaStreamSynchronize(e.stream);
-  for (auto &pr : e.pending_pass_events) {
+  for (auto &pp : e.pending_pass_events) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) e.pass_ms += ms;
-    e.event_pool.push_back(pr.first);
-    e.event_pool.push_back(pr.second);
+    if (cudaEventElapsedTime(&ms, pp.begin, pp.end) == cudaSuccess) {
+      e.pass_ms += ms;
+      if (pp.carries_swap) e.fused_swap_pass_ms += ms;
+      if (pp.generation == e.plan_generation && pp.index >= 0 && (size_t)pp.index < e.last_plan.size()) {
+        if (e.last_plan_ms.size() < e.last_plan.size()) e.last_plan_ms.resize(e.last_plan.size(), -1.0);
+        e.last_plan_ms[(size_t)pp.index] = ms;
+      }
+    }
+    e.event_pool.push_back(pp.begin);
+    e.event_pool.push_back(pp.end);
   }
   e.pending_pass_events.clear();
   for (auto &pr : e.pending_xchg_events) {
@@ -209,16 +228,6 @@ static void fold_events(Engine &e) {
     e.event_pool.push_back(pr.second);
   }
   e.pending_xchg_events.clear();
-  for (auto &pr : e.pending_fused_events) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
-      e.fused_swap_pass_ms += ms;
-      e.pass_ms += ms;
-    }
-    e.event_pool.push_back(pr.first);
-    e.event_pool.push_back(pr.second);
-  }
-  e.pending_fused_events.clear();
 }
 
 // ------------------------------------------------------------------ scratch buffer
@@ -273,9 +282,8 @@ static void trace_gates(Engine &e, const std::vector<PhysGate> &gates) {
 
 // smallest tile the selected kernel variant runs on (only ldg8 is instantiated below 12 bits)
 static int min_tile_bits(const Engine &e) {
-  if (e.opt.tile_kernel == 3) return std::min(QCS_MIN_TILE_BITS, e.opt.tile_bits);
-  if (e.opt.tile_kernel == 0 && e.opt.fast_math) return 11;  // ldg under math=fast: 11- and 12-bit tiles
-  return QCS_TILE_BITS;
+  if (e.opt.tile_kernel == 3 || e.opt.tile_kernel == 0) return std::min(QCS_MIN_TILE_BITS, e.opt.tile_bits);
+  return QCS_TILE_BITS;  // the TMA-staged kernels exist for 12-bit tiles only
 }
 
 static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysGate> &gates) {
@@ -301,25 +309,18 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
 // Launches planned passes [first, last); `swap` (may be null) rides on the stores of the last one.
 static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t first, size_t last,
                          const SwapStore *swap, int swap_lpos = -1, int swap_gpos = -1) {
-  if (first >= last) return QCS_CUDA_OK;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   const bool timed = e.timing && !e.opt.dryrun;
-  if (timed) {
-    ev0 = get_event(e);
-    ev1 = get_event(e);
-    cudaEventRecord(ev0, e.stream);
-  }
   for (size_t k = first; k < last; k++) {
     const PassPlan &p = plan[k];
+    const bool carries = swap && k + 1 == last;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (timed) {
+      ev0 = get_event(e);
+      ev1 = get_event(e);
+      cudaEventRecord(ev0, e.stream);
+    }
     if (!e.opt.dryrun) {
-      if (swap && k + 1 == last) {
-        if (timed) {  // the plain passes so far; the one that carries the swap is timed on its own
-          cudaEventRecord(ev1, e.stream);
-          e.pending_pass_events.emplace_back(ev0, ev1);
-          ev0 = get_event(e);
-          ev1 = get_event(e);
-          cudaEventRecord(ev0, e.stream);
-        }
+      if (carries) {
         SwapStore sw = *swap;
         sw.lpos_in_tile = 0;
         for (int pos : p.tile_positions)
@@ -339,15 +340,16 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
     e.pass_bytes += bytes;
     e.pass_flops_per_amp += p.flops_per_amp;
     e.last_plan.push_back(p);
-    if (swap && k + 1 == last) {
+    if (carries) {
       e.last_plan.back().swap_lpos = swap_lpos;
       e.last_plan.back().swap_gpos = swap_gpos;
     }
-  }
-  if (ev0) {
-    cudaEventRecord(ev1, e.stream);
-    (swap ? e.pending_fused_events : e.pending_pass_events).emplace_back(ev0, ev1);
-    if (e.pending_pass_events.size() > 512) fold_events(e);
+    if (timed) {
+      cudaEventRecord(ev1, e.stream);
+      e.pending_pass_events.push_back(Engine::PendingPass{ev0, ev1, carries, e.plan_generation,
+                                                          (int)e.last_plan.size() - 1});
+      if (e.pending_pass_events.size() > 512) fold_events(e);
+    }
   }
   return QCS_CUDA_OK;
 }
@@ -643,12 +645,36 @@ static size_t cancel_exact_pairs(std::vector<HostGate> &q) {
 
 static int canonicalize(Engine &e);
 
+static int flush_queue(Engine &e);
+
+// Executes everything queued.  A failure part-way (allocation, launch, NCCL, a swap handshake that
+// timed out) leaves the amplitudes partially updated and the rest of the queue dropped: the engine is
+// then POISONED -- this and every later call that needs the amplitudes returns the error instead of
+// silently computing on a state no gate sequence produces.
 static int flush(Engine &e) {
+  if (e.poisoned)
+    return set_error(QCS_CUDA_ERR_CUDA, "engine unusable after an earlier failure: %s", e.poison_reason.c_str());
+  int rc = flush_queue(e);
+  if (rc == QCS_CUDA_OK && e.swap_status_pending) {
+    rc = check_cuda(cudaStreamSynchronize(e.stream), "cudaStreamSynchronize");
+    if (rc == QCS_CUDA_OK) rc = dist_check_fused_swaps(e);
+  }
+  if (rc != QCS_CUDA_OK) {
+    e.poisoned = true;
+    e.poison_reason = qcs_cuda_last_error();
+  }
+  return rc;
+}
+
+static int flush_queue(Engine &e) {
   if (e.queue.empty()) return QCS_CUDA_OK;
   e.carried_sum_valid = false;  // gates are about to change the amplitudes
   std::vector<HostGate> q;
   q.swap(e.queue);
+  fold_events(e);  // per-pass times of the previous flush are final before its plan is dropped
   e.last_plan.clear();
+  e.last_plan_ms.clear();
+  e.plan_generation++;
   if (e.opt.sem == SEM_CORRECTED && e.opt.peephole) {
     e.gates_cancelled += (long long)cancel_exact_pairs(q);
     if (q.empty()) return QCS_CUDA_OK;
@@ -739,10 +765,12 @@ static int require_data(const Engine &e) {
 // Exact left-to-right sum of |a|^2 over the whole logical state (all ranks),
 // optionally masked to indices with bit `pos` clear.  Leaves chunk_exact on
 // every rank; *total is the same on every rank.
+// pos = SEL_RE / SEL_IM (kernels.h): the sequential sum of the amplitudes' real / imaginary parts
+// instead (q_apply_diffusion, reference src/q_gates.c:334-336); same chaining across ranks.
 static int exact_total(Engine &e, int pos, double *total) {
   DistContext &d = dist();
   double *res = e.ws.result;
-  int mask_local = (pos >= 0 && pos < e.nl) ? pos : -1;
+  int mask_local = pos <= SEL_RE ? pos : (pos >= 0 && pos < e.nl) ? pos : SEL_ALL;
   // a masked GLOBAL position: whole shards either count or not
   const bool shard_counts = !(pos >= e.nl && ((e.shard_base >> pos) & 1ull));
   if (!d.active) {
@@ -830,9 +858,31 @@ const char *qcs_cuda_last_error(void) { return g_error; }
 
 int qcs_cuda_set_default(const char *key, const char *value) {
   if (!key) return set_error(QCS_CUDA_ERR_INVALID, "null key");
+  std::lock_guard<std::mutex> lock(globals_mutex());
   if (!value) defaults().erase(key);
   else defaults()[key] = value;
   return QCS_CUDA_OK;
+}
+
+long qcs_cuda_get_default(const char *key, char *buf, long cap) {
+  if (!key) return -1;
+  std::lock_guard<std::mutex> lock(globals_mutex());
+  auto it = defaults().find(key);
+  if (it == defaults().end()) return -1;
+  if (buf && cap > 0) {
+    const long n = (long)it->second.size() < cap - 1 ? (long)it->second.size() : cap - 1;
+    std::memcpy(buf, it->second.data(), (size_t)n);
+    buf[n] = 0;
+  }
+  return (long)it->second.size();
+}
+
+long qcs_cuda_trim_pool(void) {
+  std::lock_guard<std::mutex> lock(globals_mutex());
+  long freed = 0;
+  for (auto &p : g_pool) freed += (long)p.bytes;
+  pool_trim_locked();
+  return freed;
 }
 
 int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
@@ -893,7 +943,8 @@ int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
                          up(n_chunks * sizeof(double)), up((n_chunks + 1) * sizeof(double)),
                          up(n_chunks * sizeof(double)), up(n_chunks), up((n_chunks + 1) * sizeof(double)),
                          up((n_chunks / 1024 + 2) * sizeof(double)), up((n_chunks / 1024 + 2) * sizeof(double)),
-                         up(n_chunks / 1024 + 2)};
+                         up(n_chunks / 1024 + 2), up(n_chunks * sizeof(double)), up(n_chunks * sizeof(double)),
+                         up(n_chunks * sizeof(double))};
     size_t total = 0;
     for (size_t b : sz) total += b;
     e->ws_slab_bytes = total;
@@ -910,7 +961,10 @@ int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
     ws.chunk_exact = (double *)p; p += sz[8];
     ws.group_sum = (double *)p; p += sz[9];
     ws.group_exact = (double *)p; p += sz[10];
-    ws.group_flag = (unsigned char *)p;
+    ws.group_flag = (unsigned char *)p; p += sz[11];
+    ws.chunk_sum2 = (double *)p; p += sz[12];
+    ws.chunk_abs = (double *)p; p += sz[13];
+    ws.chunk_abs2 = (double *)p;
   }
   if ((rc = check_cuda(cudaMemsetAsync(ws.result, 0, RES_COUNT * sizeof(double), e->stream), "cudaMemset")))
     return fail(rc);
@@ -936,9 +990,8 @@ void qcs_cuda_state_destroy(qcs_cuda_engine *e) {
     dist_barrier(*e);  // nobody still addresses this buffer
     dist_close_peers(*e);
   }
-  for (auto &pr : e->pending_pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (auto &pp : e->pending_pass_events) { cudaEventDestroy(pp.begin); cudaEventDestroy(pp.end); }
   for (auto &pr : e->pending_xchg_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-  for (auto &pr : e->pending_fused_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);
   for (auto ev : e->markers) if (ev) cudaEventDestroy(ev);
   pool_free(e->live, e->local_size * sizeof(double2));
@@ -1028,16 +1081,42 @@ int qcs_cuda_diffusion(qcs_cuda_engine *e) {
   RC(flush(*e));
   if (e->opt.dryrun) return QCS_CUDA_OK;
   double *res = e->ws.result;
-  // sum of all amplitudes: carried over from the previous diffusion's write pass when nothing but
-  // phase flips touched the state since (Grover's loop), else one read pass
-  if (!e->carried_sum_valid) {
-    CK(launch_complex_sum(e->live, e->local_size, e->ws, e->stream));
-    e->kernel_launches += 2;
-    e->algorithmic_bytes += 16.0 * (double)e->local_size;
+  if (e->opt.fast_math) {
+    // math=fast: tree sums (more accurate than the reference's sequential sum, hence NOT within 1e-12
+    // of it on large registers -- DESIGN.md); the write pass of one diffusion carries the sum for the
+    // next when nothing but phase flips touched the state since (Grover's loop)
+    if (!e->carried_sum_valid) {
+      CK(launch_complex_sum(e->live, e->local_size, e->ws, e->stream));
+      e->kernel_launches += 2;
+      e->algorithmic_bytes += 16.0 * (double)e->local_size;
+    }
+    CK(cudaMemcpyAsync(res + RES_SUM_RE, res + RES_LOCAL_SUM_RE, 2 * sizeof(double),
+                       cudaMemcpyDeviceToDevice, e->stream));
+    if (dist().active) RC(dist_allreduce_sum(*e, res + RES_SUM_RE, 2));
+  } else if (!dist().active) {
+    // The reference's left-to-right sums of the real and of the imaginary parts, bit for bit
+    // (kernels_reduce.cu, "Signed sums"); everything stays on the stream, no host round trip.
+    CK(launch_chunk_sums_complex(e->live, e->local_size, e->ws, e->stream));
+    e->kernel_launches++;
+    for (int comp = 0; comp < 2; comp++) {
+      const int sel = comp == 0 ? SEL_RE : SEL_IM;
+      CK(launch_chunk_deltas(e->live, e->local_size, sel, res + RES_ZERO, e->ws, e->stream));
+      CK(launch_chunk_resolve(e->live, e->local_size, sel, res + RES_ZERO, e->ws, e->stream));
+      CK(cudaMemcpyAsync(res + RES_SUM_RE + comp, res + RES_EXACT_TOTAL, sizeof(double),
+                         cudaMemcpyDeviceToDevice, e->stream));
+      e->kernel_launches += 5;
+    }
+    e->algorithmic_bytes += 3 * 16.0 * (double)e->local_size;
+  } else {
+    // sharded: rank r continues the sum where rank r-1 stopped, in basis-index order
+    RC(canonicalize(*e));
+    double sum[2] = {0.0, 0.0};
+    RC(exact_total(*e, SEL_RE, &sum[0]));
+    RC(exact_total(*e, SEL_IM, &sum[1]));
+    CK(cudaMemcpyAsync(res + RES_SUM_RE, sum, 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));  // `sum` is a stack buffer
+    e->algorithmic_bytes += 4 * 16.0 * (double)e->local_size;
   }
-  CK(cudaMemcpyAsync(res + RES_SUM_RE, res + RES_LOCAL_SUM_RE, 2 * sizeof(double),
-                     cudaMemcpyDeviceToDevice, e->stream));
-  if (dist().active) RC(dist_allreduce_sum(*e, res + RES_SUM_RE, 2));
   CK(launch_diffusion_mean(e->ws, e->opt.sem == SEM_CORRECTED, (double)(1ull << e->n), e->stream));
   if (e->opt.sem == SEM_REFERENCE) {
     // new values go to the other buffer, then the buffers trade roles (:348-355)
@@ -1045,10 +1124,13 @@ int qcs_cuda_diffusion(qcs_cuda_engine *e) {
     CK(launch_diffusion_write(e->live, e->scratch, e->local_size, e->ws, e->stream));
     std::swap(e->live, e->scratch);
     e->kernel_launches += 2;
-  } else {
+  } else if (e->opt.fast_math) {
     CK(launch_diffusion_write_sum(e->live, e->live, e->local_size, e->ws, e->stream));
     e->carried_sum_valid = true;
     e->kernel_launches += 3;
+  } else {
+    CK(launch_diffusion_write(e->live, e->live, e->local_size, e->ws, e->stream));
+    e->kernel_launches += 2;
   }
   e->algorithmic_bytes += 32.0 * (double)e->local_size;
   return QCS_CUDA_OK;
@@ -1354,6 +1436,19 @@ long qcs_cuda_last_plan_swap(qcs_cuda_engine *e, long pass_index, int *lpos, int
   if (lpos) *lpos = p.swap_lpos;
   if (gpos) *gpos = p.swap_gpos;
   return 1;
+}
+
+long qcs_cuda_last_plan_pass_info(qcs_cuda_engine *e, long pass_index, double *ms, double *flops_per_amp,
+                                  int *tile_bits, int *segments) {
+  if (!e) return 0;
+  fold_events(*e);
+  if (pass_index < 0 || pass_index >= (long)e->last_plan.size()) return (long)e->last_plan.size();
+  const PassPlan &p = e->last_plan[(size_t)pass_index];
+  if (ms) *ms = (size_t)pass_index < e->last_plan_ms.size() ? e->last_plan_ms[(size_t)pass_index] : -1.0;
+  if (flops_per_amp) *flops_per_amp = p.flops_per_amp;
+  if (tile_bits) *tile_bits = p.params.tile_bits;
+  if (segments) *segments = p.params.n_segments;
+  return (long)e->last_plan.size();
 }
 
 long qcs_cuda_last_plan_raw(qcs_cuda_engine *e, long pass_index, void *buf, long cap) {

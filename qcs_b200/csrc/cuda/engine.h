@@ -64,6 +64,12 @@ struct Engine {
   uint32_t *tile_flags = nullptr;         // one word per tile: handshake of passes that swap on the way out
   std::vector<uint32_t *> peer_flags;     // every rank's tile_flags, peer-mapped
   uint32_t swap_epoch = 0;
+  uint32_t *swap_abort_flag = nullptr;    // device word behind tile_flags: a CTA gave up waiting for its partner
+  int *swap_status_host = nullptr;        // pinned: all-reduced abort words of the last swap-carrying pass
+  bool swap_status_pending = false;       // a status copy is in flight on the stream
+  bool poisoned = false;                  // a failed flush / swap left the amplitudes undefined: every later
+                                          // call that needs them returns the error
+  std::string poison_reason;
   bool carried_sum_valid = false;  // ws.result[RES_LOCAL_SUM_*] holds the sum of this shard's amplitudes
   ReduceWorkspace ws{};
   void *ws_slab = nullptr;       // one allocation backing every array of ws
@@ -89,9 +95,13 @@ struct Engine {
   double algorithmic_bytes = 0, pass_bytes = 0, pass_ms = 0, exchange_bytes = 0, exchange_ms = 0;
   double pass_flops_per_amp = 0;  // planner's FP64 operation count per amplitude, summed over executed passes
   double fused_swap_pass_ms = 0;  // device time of the passes that carried a swap (also in pass_ms)
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_fused_events;
   bool timing = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_pass_events;
+  // one event pair per launched pass (timing on): folded into pass_ms / fused_swap_pass_ms and, for the
+  // passes of the most recent flush, into last_plan_ms (per-pass roofline figures of bench.py)
+  struct PendingPass { cudaEvent_t begin, end; bool carries_swap; long long generation; int index; };
+  std::vector<PendingPass> pending_pass_events;
+  long long plan_generation = 0;        // bumped whenever last_plan is cleared
+  std::vector<double> last_plan_ms;     // device time of last_plan[k], -1 where not measured
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_xchg_events;
   std::vector<cudaEvent_t> event_pool;
   cudaEvent_t markers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -114,6 +124,7 @@ bool dist_p2p_available(const Engine &e);
 int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos);
 bool dist_fused_swap_args(Engine &e, int lpos, int gpos, SwapStore &sw);
 int dist_after_fused_swap(Engine &e);
+int dist_check_fused_swaps(Engine &e);  // after a stream synchronisation: error if a handshake wait timed out
 void dist_close_peers(Engine &e);
 
 }  // namespace qcs

@@ -21,12 +21,18 @@ struct SwapStore {
   uint32_t lpos;              // local position traded for the partner-selecting rank bit
   uint32_t my_gbit;           // my value of that rank bit
   uint32_t lpos_in_tile;      // lpos is one of the pass's tile positions
+  uint32_t *abort_flag;       // my own device word: set when a CTA gave up waiting for the partner (the tile
+                              // is then NOT stored and the engine reports QCS_CUDA_ERR_CUDA); later CTAs bail out
+  unsigned long long spin_limit;  // clock64 ticks a CTA waits for the partner's signal before giving up
 };
 // fast (ldg8 only): the fused-multiply-add interpreter; `params` must come from a planner run with
 // PlannerConfig::fast_math (fan entries carry product tables instead of single phases).
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
                               cudaStream_t stream, int variant, const SwapStore *swap = nullptr,
                               bool fast = false);
+
+// multiprocessor count of the current device (cached per device); grids are sized from it
+int device_sm_count();
 
 // kernels_simple.cu: one launch per gate (fusion off, shards below one tile) ---
 cudaError_t launch_simple_gate(double2 *state, const DGate &g, int n_local,
@@ -44,6 +50,9 @@ struct ReduceWorkspace {
   long long *iresult;      // device, 2 long longs
   // exact sequential-prefix machinery (chunked)
   double *chunk_sum;       // device, n_chunks
+  double *chunk_sum2;      // device, n_chunks: the imaginary parts' chunk sums (diffusion)
+  double *chunk_abs;       // device, n_chunks: sums of |re| per chunk (signed sums: "adds nothing" test)
+  double *chunk_abs2;      // device, n_chunks: sums of |im| per chunk
   double *chunk_approx;    // device, n_chunks + 1
   double *chunk_delta;     // device, n_chunks
   unsigned char *chunk_flag;  // device, n_chunks
@@ -54,6 +63,10 @@ struct ReduceWorkspace {
   size_t n_chunks_cap;
 };
 enum { REDUCE_MAX_BLOCKS = 4096, SEQ_CHUNK = 1024 };
+// What the exact sequential sums add up (the `mask_pos` argument below): a position >= 0 = |a_i|^2 over
+// the indices with that bit clear, SEL_ALL = every |a_i|^2, SEL_RE / SEL_IM = the real / imaginary parts
+// of the amplitudes themselves (signed; q_apply_diffusion, reference src/q_gates.c:334-336).
+enum { SEL_ALL = -1, SEL_RE = -2, SEL_IM = -3 };
 
 cudaError_t launch_init_state(double2 *state, uint64_t n_amps, bool set_one, cudaStream_t s);
 cudaError_t launch_complex_sum(const double2 *state, uint64_t n_amps, ReduceWorkspace &ws,
@@ -97,6 +110,9 @@ enum { RES_SUM_RE = 0, RES_SUM_IM = 1, RES_TWO_MEAN_RE = 2, RES_TWO_MEAN_IM = 3,
        RES_LOCAL_SUM_RE = 9, RES_LOCAL_SUM_IM = 10, RES_COUNT = 16 };
 cudaError_t launch_chunk_sums(const double2 *state, uint64_t n_amps, int mask_pos,
                               ReduceWorkspace &ws, cudaStream_t s);
+// K1 for SEL_RE and SEL_IM in one read of the shard (no result[RES_APPROX_TOTAL])
+cudaError_t launch_chunk_sums_complex(const double2 *state, uint64_t n_amps, ReduceWorkspace &ws,
+                                      cudaStream_t s);
 cudaError_t launch_chunk_deltas(const double2 *state, uint64_t n_amps, int mask_pos,
                                 const double *approx_start_dev, ReduceWorkspace &ws,
                                 cudaStream_t s);

@@ -211,24 +211,47 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 // ---------------------------------------------------------------------------
 #define QCS_FAST 0
 #define QCS_R 4
-#define QCS_T 12
 #define QCS_CT (1 << (QCS_T - QCS_R))
-#define QCS_MIN_CTAS 2
 #define QCS_NREG_STR "16"
 #define QCS_LIST(x) QCS4_##x
-#define QCS_NAME(x) x##_r4
 #define QCS_WITH_LDG 1
+
+#define QCS_T 12
+#define QCS_MIN_CTAS 2
+#define QCS_NAME(x) x##_r4
 #define QCS_WITH_TMA 1
 #include "fused_body.inc"
-#undef QCS_R
 #undef QCS_T
-#undef QCS_CT
 #undef QCS_MIN_CTAS
+#undef QCS_NAME
+#undef QCS_WITH_TMA
+
+// 16 amplitudes per thread on small tiles: 4 x 128 or 8 x 64 threads per SM.  Half the warps of ldg8,
+// but every per-gate cost (dispatch, fan-entry bookkeeping) is spread over twice the amplitudes and a
+// segment pairs on four positions.
+#define QCS_WITH_TMA 0
+#define QCS_T 11
+#define QCS_MIN_CTAS 3
+#define QCS_NAME(x) x##_r4_t11
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+
+#define QCS_T 10
+#define QCS_MIN_CTAS 8
+#define QCS_NAME(x) x##_r4_t10
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+#undef QCS_WITH_TMA
+
+#undef QCS_R
+#undef QCS_CT
 #undef QCS_NREG_STR
 #undef QCS_LIST
-#undef QCS_NAME
 #undef QCS_WITH_LDG
-#undef QCS_WITH_TMA
 
 #define QCS_R 3
 #define QCS_NREG_STR "8"
@@ -326,6 +349,14 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 #undef QCS_T
 #undef QCS_MIN_CTAS
 #undef QCS_NAME
+
+#define QCS_T 10
+#define QCS_MIN_CTAS 8
+#define QCS_NAME(x) x##_r4f_t10
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
 #undef QCS_WITH_TMA
 
 #undef QCS_R
@@ -365,94 +396,93 @@ static int tile_row_bits(const PassParams &p) {
 
 }  // namespace
 
+using LdgKernel = void (*)(double2 *, const PassParams, uint32_t, uint32_t, uint32_t, const SwapStore);
+
+// [math=fast][16 amplitudes per thread][tile bits - 10]
+static LdgKernel ldg_kernel(bool fast, bool r4, int T) {
+  static const LdgKernel table[2][2][3] = {
+      {{fused_pass_ldg_r3_t10, fused_pass_ldg_r3_t11, fused_pass_ldg_r3},
+       {fused_pass_ldg_r4_t10, fused_pass_ldg_r4_t11, fused_pass_ldg_r4}},
+      {{fused_pass_ldg_r3f_t10, fused_pass_ldg_r3f_t11, fused_pass_ldg_r3f},
+       {fused_pass_ldg_r4f_t10, fused_pass_ldg_r4f_t11, fused_pass_ldg_r4f}}};
+  return table[fast ? 1 : 0][r4 ? 1 : 0][T - QCS_MIN_TILE_BITS];
+}
+
+// Per-device launch state (engines on different GPUs may live in one process).
+struct DeviceLaunchState {
+  int sm_count = 0;
+  bool ldg_configured[2][2][3] = {};
+  bool tma_configured[2] = {false, false};
+};
+static DeviceLaunchState *device_launch_state(cudaError_t *err) {
+  static DeviceLaunchState states[64];
+  int dev = 0;
+  *err = cudaGetDevice(&dev);
+  if (*err != cudaSuccess) return nullptr;
+  if (dev < 0 || dev >= 64) {
+    *err = cudaErrorInvalidDevice;
+    return nullptr;
+  }
+  DeviceLaunchState *s = &states[dev];
+  if (s->sm_count == 0) {
+    int sms = 0;
+    *err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (*err != cudaSuccess) return nullptr;
+    s->sm_count = sms;
+  }
+  return s;
+}
+
+int device_sm_count() {
+  cudaError_t err;
+  DeviceLaunchState *s = device_launch_state(&err);
+  return s ? s->sm_count : 148;
+}
+
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
                               cudaStream_t stream, int variant, const SwapStore *swap, bool fast) {
-  if (swap && variant != 0 && variant != 3) return cudaErrorInvalidValue;  // ldg kernels only
-  if (fast && variant != 3 && variant != 0) return cudaErrorInvalidValue;  // math=fast: ldg8 and ldg only
+  if (variant < 0 || variant > 3) return cudaErrorInvalidValue;
+  const bool ldg = variant == 0 || variant == 3;
+  if ((swap || fast) && !ldg) return cudaErrorInvalidValue;  // plain-load kernels only
   SwapStore sw{};
   if (swap) sw = *swap;
   const int T = params.tile_bits;
   if (T < QCS_MIN_TILE_BITS || T > QCS_TILE_BITS || T > n_local) return cudaErrorInvalidValue;
-  // only ldg8 has small tiles (and, under math=fast, ldg at 11 bits)
-  if (T != QCS_TILE_BITS && variant != 3 && !(fast && variant == 0 && T == 11)) return cudaErrorInvalidValue;
-  const unsigned n_tiles = 1u << (n_local - T);
-  static int sm_count = 0;
-  static bool configured[11] = {false, false, false, false, false, false, false, false, false, false, false};
-  if (variant < 0 || variant > 3) return cudaErrorInvalidValue;
+  if (T != QCS_TILE_BITS && !ldg) return cudaErrorInvalidValue;  // the TMA kernels exist for 12-bit tiles only
   if ((variant >= 2) != (params.reg_bits == 3)) return cudaErrorInvalidValue;
-  if (sm_count == 0) {
-    int dev = 0, sms = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    sm_count = sms;
+  const unsigned n_tiles = 1u << (n_local - T);
+  cudaError_t e;
+  DeviceLaunchState *dls = device_launch_state(&e);
+  if (!dls) return e;
+  const int sm_count = dls->sm_count;
+  const uint32_t pf = prefetch_distance(), st = stagger_ns();
+  if (ldg) {
+    const bool r4 = variant == 0;
+    // math=fast: the tile + one 16-byte factor per uniform fan behind it
+    const size_t smem = ((size_t)16 << T) + (fast ? 16 * QCS_MAX_PASS_FANS : 0);
+    LdgKernel k = ldg_kernel(fast, r4, T);
+    bool &configured = dls->ldg_configured[fast ? 1 : 0][r4 ? 1 : 0][T - QCS_MIN_TILE_BITS];
+    if (!configured) {
+      e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    k<<<n_tiles, 1u << (T - params.reg_bits), smem, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
+    return cudaGetLastError();
   }
   const size_t smem_tma = (size_t)kSlots * kTileBytes + 128;  // slots + barriers + tile origins
-  // math=fast: the tile + one 16-byte factor per uniform fan behind it
-  const size_t smem_ldg = ((size_t)16 << T) + (fast ? 16 * QCS_MAX_PASS_FANS : 0);
-  // 3, 4, 5: ldg8 at 12, 11, 10 bits; 6, 7, 8: the same with math=fast
-  // 9, 10: ldg (16 amplitudes per thread) with math=fast at 12, 11 bits
-  const int slot = variant == 3 ? 3 + (QCS_TILE_BITS - T) + (fast ? 3 : 0)
-                                : (fast && variant == 0) ? 9 + (QCS_TILE_BITS - T) : variant;
-  if (!configured[slot]) {
-    cudaError_t e;
-    if (fast && variant == 0)
-      e = cudaFuncSetAttribute(T == 12 ? fused_pass_ldg_r4f : fused_pass_ldg_r4f_t11,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ldg);
-    else if (fast)
-      e = cudaFuncSetAttribute(T == 12 ? fused_pass_ldg_r3f : T == 11 ? fused_pass_ldg_r3f_t11 : fused_pass_ldg_r3f_t10,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ldg);
-    else if (variant == 0)
-      e = cudaFuncSetAttribute(fused_pass_ldg_r4, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem_ldg);
-    else if (variant == 1)
-      e = cudaFuncSetAttribute(fused_pass_tma_r4, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem_tma);
-    else if (variant == 2)
-      e = cudaFuncSetAttribute(fused_pass_tma_r3, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem_tma);
-    else if (T == 12)
-      e = cudaFuncSetAttribute(fused_pass_ldg_r3, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem_ldg);
-    else if (T == 11)
-      e = cudaFuncSetAttribute(fused_pass_ldg_r3_t11, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem_ldg);
-    else
-      e = cudaFuncSetAttribute(fused_pass_ldg_r3_t10, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem_ldg);
+  bool &configured = dls->tma_configured[variant - 1];
+  if (!configured) {
+    e = cudaFuncSetAttribute(variant == 1 ? fused_pass_tma_r4 : fused_pass_tma_r3,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
     if (e != cudaSuccess) return e;
-    configured[slot] = true;
+    configured = true;
   }
   const unsigned grid = n_tiles < (unsigned)sm_count ? n_tiles : (unsigned)sm_count;
-  const uint32_t pf = prefetch_distance(), st = stagger_ns();
-  if (fast && variant == 0) {
-    if (T == 12)
-      fused_pass_ldg_r4f<<<n_tiles, 256, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
-    else
-      fused_pass_ldg_r4f_t11<<<n_tiles, 128, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
-  } else if (fast) {
-    if (T == 12)
-      fused_pass_ldg_r3f<<<n_tiles, 512, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
-    else if (T == 11)
-      fused_pass_ldg_r3f_t11<<<n_tiles, 256, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
-    else
-      fused_pass_ldg_r3f_t10<<<n_tiles, 128, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
-  } else if (variant == 0) {
-    fused_pass_ldg_r4<<<n_tiles, 256, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
-  } else if (variant == 1) {
-    fused_pass_tma_r4<<<grid, 256 + 32, smem_tma, stream>>>(state, params, n_tiles,
-                                                            (uint32_t)tile_row_bits(params));
-  } else if (variant == 2) {
-    fused_pass_tma_r3<<<grid, 512 + 32, smem_tma, stream>>>(state, params, n_tiles,
-                                                            (uint32_t)tile_row_bits(params));
-  } else if (T == 12) {
-    fused_pass_ldg_r3<<<n_tiles, 512, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
-  } else if (T == 11) {
-    fused_pass_ldg_r3_t11<<<n_tiles, 256, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
-  } else {
-    fused_pass_ldg_r3_t10<<<n_tiles, 128, smem_ldg, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
-  }
+  if (variant == 1)
+    fused_pass_tma_r4<<<grid, 256 + 32, smem_tma, stream>>>(state, params, n_tiles, (uint32_t)tile_row_bits(params));
+  else
+    fused_pass_tma_r3<<<grid, 512 + 32, smem_tma, stream>>>(state, params, n_tiles, (uint32_t)tile_row_bits(params));
   return cudaGetLastError();
 }
 

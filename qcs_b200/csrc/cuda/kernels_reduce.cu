@@ -27,6 +27,19 @@
 // unsafe (tie, binade crossing, wrong binade guess).  The result is the
 // reference's sequence of partial sums, bit for bit, at chunk boundaries;
 // the sampler then replays inside one chunk per shot.
+//
+// Signed sums.  Grover's diffusion sums the amplitudes themselves, real and
+// imaginary parts, left to right (src/q_gates.c:334-336).  The same argument
+// holds for signed terms as long as the running sum keeps its sign and binade
+// THROUGHOUT a chunk; that is guaranteed when every term of the chunk has the
+// sign of the running sum (monotone: checking the end points is enough), so a
+// chunk whose terms have mixed signs, or oppose the running sum, is flagged and
+// replayed term by term (`sel` = SEL_RE / SEL_IM below).  Grover's states have
+// all non-solution amplitudes equal, so the fast path covers them; after a
+// generic circuit most chunks replay (one warp, ~2^n dependent additions).
+// A tree sum is NOT good enough here: the reference's sequential sum of 2^n
+// equal terms drifts from the true mean (6e-10 relative after the 804
+// iterations at 20 qubits), and parity is with the reference.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -52,6 +65,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 __device__ __forceinline__ int exponent_of(double x) {
   return (__double2hiint(x) >> 20) & 0x7ff;
+}
+// same sign and same binade (for the non-negative sums of |a|^2 this is the exponent test)
+__device__ __forceinline__ bool same_binade(double a, double b) {
+  return (((unsigned)__double2hiint(a) ^ (unsigned)__double2hiint(b)) >> 20) == 0u;
 }
 
 unsigned grid_for(uint64_t items, int per_block) {
@@ -320,8 +337,14 @@ __global__ void argmax_final_kernel(const double *partials, const long long *ipa
 // ---------------------------------------------------------------- exact prefix
 enum { FLAG_TIE = 1, FLAG_CROSS = 2, FLAG_ZERO = 4 };
 
+// Term i of the sequential sum selected by `mask_pos` (kernels.h): >= 0 |a_i|^2 over indices with that
+// bit clear, SEL_ALL |a_i|^2, SEL_RE / SEL_IM the real / imaginary part of a_i (signed).
 __device__ __forceinline__ double masked_norm(const double2 *__restrict__ state, uint64_t i,
                                               int mask_pos) {
+  if (mask_pos <= SEL_RE) {
+    const double2 a = __ldg(state + i);
+    return mask_pos == SEL_RE ? a.x : a.y;
+  }
   if (mask_pos >= 0 && ((i >> mask_pos) & 1ull)) return 0.0;
   return norm_sq(__ldg(state + i));
 }
@@ -329,17 +352,55 @@ __device__ __forceinline__ double masked_norm(const double2 *__restrict__ state,
 // K1: plain (tree) sum of each 1024-term chunk; one warp per chunk.
 __global__ void __launch_bounds__(256)
 chunk_sum_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mask_pos,
-                 double *chunk_sum) {
+                 double *chunk_sum, double *chunk_abs) {
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (uint64_t c = warp; c < n_chunks; c += n_warps) {
-    double s = 0.0;
+    double s = 0.0, sa = 0.0;
 #pragma unroll 8
-    for (int j = 0; j < SEQ_CHUNK / 32; j++)
-      s += masked_norm(state, c * SEQ_CHUNK + (uint64_t)j * 32 + lane, mask_pos);
+    for (int j = 0; j < SEQ_CHUNK / 32; j++) {
+      const double p = masked_norm(state, c * SEQ_CHUNK + (uint64_t)j * 32 + lane, mask_pos);
+      s += p;
+      sa += fabs(p);
+    }
     s = warp_sum(s);
-    if (lane == 0) chunk_sum[c] = s;
+    if (chunk_abs) sa = warp_sum(sa);
+    if (lane == 0) {
+      chunk_sum[c] = s;
+      if (chunk_abs) chunk_abs[c] = sa;  // signed terms: "all zero" cannot be read off a sum that may cancel
+    }
+  }
+}
+
+// K1 for both components of the amplitudes in one read (diffusion): tree sums and sums of magnitudes
+// of the real parts (sum_re, abs_re) and of the imaginary parts (sum_im, abs_im) per chunk.
+__global__ void __launch_bounds__(256)
+chunk_sum_complex_kernel(const double2 *__restrict__ state, uint64_t n_chunks, double *sum_re,
+                         double *abs_re, double *sum_im, double *abs_im) {
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t c = warp; c < n_chunks; c += n_warps) {
+    double sr = 0.0, si = 0.0, ar = 0.0, ai = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < SEQ_CHUNK / 32; j++) {
+      const double2 a = __ldcs(state + c * SEQ_CHUNK + (uint64_t)j * 32 + lane);
+      sr += a.x;
+      si += a.y;
+      ar += fabs(a.x);
+      ai += fabs(a.y);
+    }
+    sr = warp_sum(sr);
+    si = warp_sum(si);
+    ar = warp_sum(ar);
+    ai = warp_sum(ai);
+    if (lane == 0) {
+      sum_re[c] = sr;
+      sum_im[c] = si;
+      abs_re[c] = ar;
+      abs_im[c] = ai;
+    }
   }
 }
 
@@ -379,6 +440,9 @@ __global__ void __launch_bounds__(128)
 chunk_delta_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mask_pos,
                    const double *__restrict__ chunk_sum, const double *__restrict__ approx,
                    double *__restrict__ delta, unsigned char *__restrict__ flag) {
+  // chunk_sum: what decides "this chunk adds nothing" -- the chunk's sum for non-negative terms, the
+  // sum of magnitudes for signed ones (the launcher passes the right array)
+  const bool is_signed = mask_pos <= SEL_RE;
   __shared__ double stage[4][32][33];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -397,8 +461,9 @@ chunk_delta_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mas
     return;
   }
   const double a1 = have ? approx[my_chunk] : 1.0;
-  const double a2 = __longlong_as_double(__double_as_longlong(a1) + 1);  // next double up (a1 >= 0)
+  const double a2 = __longlong_as_double(__double_as_longlong(a1) + 1);  // next double away from zero
   double s1 = a1, s2 = a2;
+  bool any_pos = false, any_neg = false;
   const int n_rows = (int)((n_chunks - c0) < 32 ? (n_chunks - c0) : 32);
   for (int j = 0; j < SEQ_CHUNK / 32; j++) {
 #pragma unroll 8
@@ -414,6 +479,8 @@ chunk_delta_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mas
       const double p = stage[wib][lane][k];
       s1 = __dadd_rn(s1, p);
       s2 = __dadd_rn(s2, p);
+      any_pos |= p > 0.0;
+      any_neg |= p < 0.0;
     }
     __syncwarp();
   }
@@ -423,7 +490,10 @@ chunk_delta_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mas
     unsigned char f = 0;
     if (csum == 0.0) f |= FLAG_ZERO;
     if (d1 != d2) f |= FLAG_TIE;
-    if (exponent_of(s1) != exponent_of(a1) || exponent_of(s2) != exponent_of(a1)) f |= FLAG_CROSS;
+    if (!same_binade(s1, a1) || !same_binade(s2, a1)) f |= FLAG_CROSS;
+    // signed terms: the end points only vouch for the whole chunk when the running sum is monotone,
+    // i.e. every term has the sign of the prefix it is added to
+    if (is_signed && ((any_pos && any_neg) || (any_neg && !(a1 < 0.0)) || (any_pos && !(a1 > 0.0)))) f |= FLAG_CROSS;
     delta[my_chunk] = d1;
     flag[my_chunk] = f;
   }
@@ -473,7 +543,7 @@ group_sum_kernel(const double *__restrict__ delta, const double *__restrict__ ap
   if (lane == 0) {
     unsigned char out = 0;
     if (f & (FLAG_TIE | FLAG_CROSS)) out = 1;
-    if (exponent_of(approx[first]) != exponent_of(approx[last - 1])) out = 1;
+    if (!same_binade(approx[first], approx[last - 1])) out = 1;
     gsum[g] = s;
     gflag[g] = out;
   }
@@ -504,11 +574,11 @@ __device__ __forceinline__ double walk_chunks(const double2 *__restrict__ state,
       const int f = __shfl_sync(0xffffffffu, my_f, j);
       if (lane == j) my_exact = S;
       if (f & FLAG_ZERO) continue;
-      bool ok = !(f & (FLAG_TIE | FLAG_CROSS)) && exponent_of(S) == exponent_of(a);
+      bool ok = !(f & (FLAG_TIE | FLAG_CROSS)) && same_binade(S, a);
       double Snew = S;
       if (ok) {
         Snew = __dadd_rn(S, d);
-        ok = exponent_of(Snew) == exponent_of(S);
+        ok = same_binade(Snew, S);
       }
       if (ok) {
         S = Snew;
@@ -537,11 +607,11 @@ group_resolve_kernel(const double2 *__restrict__ state, uint64_t n_chunks, uint6
   for (uint64_t g = 0; g < n_groups; g++) {
     const uint64_t first = g * RESOLVE_GROUP;
     const uint64_t last = first + RESOLVE_GROUP < n_chunks ? first + RESOLVE_GROUP : n_chunks;
-    bool clean = gflag[g] == 0 && exponent_of(S) == exponent_of(approx[first]);
+    bool clean = gflag[g] == 0 && same_binade(S, approx[first]);
     double Snew = S;
     if (clean) {
       Snew = __dadd_rn(S, gsum[g]);
-      clean = exponent_of(Snew) == exponent_of(S);
+      clean = same_binade(Snew, S);
     }
     if (lane == 0) gexact[g] = S;
     if (clean) {
@@ -721,14 +791,31 @@ cudaError_t launch_argmax_permuted(const double2 *state, uint64_t n, const Logic
   return cudaGetLastError();
 }
 
+// the arrays a selector works on: tree sums of the chunks, and what decides "adds nothing"
+static double *sums_of(ReduceWorkspace &ws, int sel) { return sel == SEL_IM ? ws.chunk_sum2 : ws.chunk_sum; }
+static double *zero_test_of(ReduceWorkspace &ws, int sel) {
+  return sel == SEL_IM ? ws.chunk_abs2 : sel == SEL_RE ? ws.chunk_abs : ws.chunk_sum;
+}
+
 cudaError_t launch_chunk_sums(const double2 *state, uint64_t n, int mask_pos,
                               ReduceWorkspace &ws, cudaStream_t s) {
   if (n < (uint64_t)SEQ_CHUNK) return cudaSuccess;  // single short chunk: resolved by replay
   const uint64_t n_chunks = n / SEQ_CHUNK;
   uint64_t blocks = (n_chunks + 7) / 8;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  chunk_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(state, n_chunks, mask_pos, ws.chunk_sum);
-  chunk_total_kernel<<<1, 1024, 0, s>>>(ws.chunk_sum, n_chunks, ws.result + RES_APPROX_TOTAL);
+  if (blocks > (unsigned)device_sm_count() * 32) blocks = (unsigned)device_sm_count() * 32;
+  chunk_sum_kernel<<<(unsigned)blocks, 256, 0, s>>>(state, n_chunks, mask_pos, sums_of(ws, mask_pos),
+                                                    mask_pos <= SEL_RE ? zero_test_of(ws, mask_pos) : nullptr);
+  chunk_total_kernel<<<1, 1024, 0, s>>>(sums_of(ws, mask_pos), n_chunks, ws.result + RES_APPROX_TOTAL);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chunk_sums_complex(const double2 *state, uint64_t n, ReduceWorkspace &ws, cudaStream_t s) {
+  if (n < (uint64_t)SEQ_CHUNK) return cudaSuccess;
+  const uint64_t n_chunks = n / SEQ_CHUNK;
+  uint64_t blocks = (n_chunks + 7) / 8;
+  if (blocks > (unsigned)device_sm_count() * 32) blocks = (unsigned)device_sm_count() * 32;
+  chunk_sum_complex_kernel<<<(unsigned)blocks, 256, 0, s>>>(state, n_chunks, ws.chunk_sum, ws.chunk_abs,
+                                                            ws.chunk_sum2, ws.chunk_abs2);
   return cudaGetLastError();
 }
 
@@ -737,10 +824,10 @@ cudaError_t launch_chunk_deltas(const double2 *state, uint64_t n, int mask_pos,
                                 cudaStream_t s) {
   if (n < (uint64_t)SEQ_CHUNK) return cudaSuccess;
   const uint64_t n_chunks = n / SEQ_CHUNK;
-  chunk_scan_kernel<<<1, 1024, 0, s>>>(ws.chunk_sum, n_chunks, approx_start_dev, ws.chunk_approx);
+  chunk_scan_kernel<<<1, 1024, 0, s>>>(sums_of(ws, mask_pos), n_chunks, approx_start_dev, ws.chunk_approx);
   const uint64_t groups = (n_chunks + 31) / 32;
   const uint64_t blocks = (groups + 3) / 4;
-  chunk_delta_kernel<<<(unsigned)blocks, 128, 0, s>>>(state, n_chunks, mask_pos, ws.chunk_sum,
+  chunk_delta_kernel<<<(unsigned)blocks, 128, 0, s>>>(state, n_chunks, mask_pos, zero_test_of(ws, mask_pos),
                                                       ws.chunk_approx, ws.chunk_delta,
                                                       ws.chunk_flag);
   return cudaGetLastError();

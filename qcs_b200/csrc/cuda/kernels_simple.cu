@@ -107,7 +107,7 @@ cudaError_t launch_swap_local_bits(double2 *state, int n_local, int a, int b, cu
   if (a == b) return cudaSuccess;
   if (a > b) { int t = a; a = b; b = t; }
   const uint64_t n_items = (1ull << n_local) >> 2;
-  const unsigned blocks = (unsigned)((n_items + 255) / 256 > 148 * 16 ? 148 * 16 : (n_items + 255) / 256);
+  const unsigned blocks = (unsigned)((n_items + 255) / 256 > (unsigned)device_sm_count() * 16 ? (unsigned)device_sm_count() * 16 : (n_items + 255) / 256);
   swap_local_bits_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(state, a, b, n_items ? n_items : 1);
   return cudaGetLastError();
 }
@@ -117,7 +117,7 @@ cudaError_t launch_simple_gate(double2 *state, const DGate &g, int n_local, uint
   if (g.kind == GK_NOP) return cudaSuccess;
   const uint64_t n_amps = 1ull << n_local;
   if (g.kind == GK_DIAG) {
-    const unsigned blocks = (unsigned)((n_amps + 255) / 256 > 148 * 16 ? 148 * 16 : (n_amps + 255) / 256);
+    const unsigned blocks = (unsigned)((n_amps + 255) / 256 > (unsigned)device_sm_count() * 16 ? (unsigned)device_sm_count() * 16 : (n_amps + 255) / 256);
     simple_diag_kernel<<<blocks, 256, 0, stream>>>(state, g, shard_base, n_amps);
     return cudaGetLastError();
   }
@@ -133,7 +133,7 @@ cudaError_t launch_simple_gate(double2 *state, const DGate &g, int n_local, uint
     }
   }
   if (n_items == 0) n_items = 1;  // 1-qubit shard with a local control cannot happen; guard anyway
-  const unsigned blocks = (unsigned)((n_items + 255) / 256 > 148 * 16 ? 148 * 16 : (n_items + 255) / 256);
+  const unsigned blocks = (unsigned)((n_items + 255) / 256 > (unsigned)device_sm_count() * 16 ? (unsigned)device_sm_count() * 16 : (n_items + 255) / 256);
   simple_pair_kernel<<<blocks, 256, 0, stream>>>(state, g, local_control, n_items);
   return cudaGetLastError();
 }

@@ -7,7 +7,7 @@ known-answer anchors listed in SURVEY.md section 8(c).
 """
 import math
 
-from oracle.pyoracle import random_circuit_script
+from qcs_b200.workloads import random_circuit_script  # workload definition, not oracle arithmetic
 
 
 def _mixed8():

@@ -115,7 +115,7 @@ def test_fast_every_target_control_pair(tile_bits):
 
 
 @pytest.mark.parametrize("reorder", ["on", "off"])
-@pytest.mark.parametrize("tile_bits", [11, 12])
+@pytest.mark.parametrize("tile_bits", [10, 11, 12])
 @pytest.mark.parametrize("n", [11, 12, 14, 17, 21])
 def test_fast_16_amplitudes_per_thread(n, tile_bits, reorder):
     """tile_kernel=ldg under math=fast: 16 amplitudes per thread, four pairing positions per segment."""

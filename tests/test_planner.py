@@ -43,6 +43,7 @@ PAIRING = {"generic", "real", "hsym", "swap"}
 
 
 @pytest.mark.parametrize("tile_kernel,reg_bits,tile_bits", [("tma", 3, 12), ("tma16", 4, 12), ("ldg", 4, 12),
+                                                            ("ldg", 4, 11), ("ldg", 4, 10),
                                                             ("ldg8", 3, 12), ("ldg8", 3, 11), ("ldg8", 3, 10)])
 @pytest.mark.parametrize("n", [12, 20, 30, 34])
 def test_plan_invariants_random_circuit(n, tile_kernel, reg_bits, tile_bits):
@@ -53,8 +54,8 @@ def test_plan_invariants_random_circuit(n, tile_kernel, reg_bits, tile_bits):
     assert sum(p["api"] for p in passes) == len(script)
     for p in passes:
         tile = p["tile"]
-        # a pass runs on the smallest tile (>= 10 bits for ldg8, else 12) that holds its pairing qubits
-        lo = 10 if tile_kernel == "ldg8" else 12
+        # a pass runs on the smallest tile (>= 10 bits for the plain-load kernels, else 12) that holds its pairing qubits
+        lo = 10 if tile_kernel in ("ldg8", "ldg") else 12
         assert lo <= len(tile) <= max(lo, tile_bits) and tile == sorted(set(tile)) and tile[:5] == [0, 1, 2, 3, 4]
         assert all(t < n for t in tile)
         assert p["nseg"] == len(p["segs"]) <= 12
@@ -156,7 +157,7 @@ def _fan_script(n, seed):
 
 
 @pytest.mark.parametrize("math", ["exact", "fast", "fast+reorder"])
-@pytest.mark.parametrize("tile_kernel,tile_bits", [("ldg8", 10), ("ldg8", 11), ("ldg8", 12), ("ldg", 11), ("ldg", 12)])
+@pytest.mark.parametrize("tile_kernel,tile_bits", [("ldg8", 10), ("ldg8", 11), ("ldg8", 12), ("ldg", 10), ("ldg", 11), ("ldg", 12)])
 @pytest.mark.parametrize("case", ["qft", "random+qft", "fans", "generic"])
 def test_descriptors_compute_the_circuit(case, tile_kernel, tile_bits, math):
     from qcs_b200 import Circuit
@@ -253,7 +254,7 @@ def test_reordered_plans_on_random_gate_soup(seed):
 
 # ---- the kernel's own view of a plan: role tables, addresses, case labels (tests/kernel_emulator.py) ---
 @pytest.mark.parametrize("math", ["exact", "fast", "fast+reorder"])
-@pytest.mark.parametrize("tile_kernel,tile_bits", [("ldg8", 10), ("ldg8", 11), ("ldg8", 12), ("ldg", 11), ("ldg", 12),
+@pytest.mark.parametrize("tile_kernel,tile_bits", [("ldg8", 10), ("ldg8", 11), ("ldg8", 12), ("ldg", 10), ("ldg", 11), ("ldg", 12),
                                                     ("tma", 12), ("tma16", 12)])
 @pytest.mark.parametrize("case", ["qft", "random+qft", "fans", "generic"])
 def test_kernel_model_computes_the_circuit(case, tile_kernel, tile_bits, math):
