@@ -97,6 +97,12 @@ static int load_options(Options &o) {
   else return set_error(QCS_CUDA_ERR_INVALID, "exchange must be p2p|nccl, got '%s'", v.c_str());
   v = option_value("fuse_swaps");
   o.fuse_swaps = !(v == "off" || v == "0");
+  v = option_value("lazy_init");
+  o.lazy_init = !(v == "off" || v == "0");
+  v = option_value("swap_store");
+  if (v == "thread" || v == "st") o.swap_bulk = false;
+  else if (v.empty() || v == "bulk") o.swap_bulk = true;
+  else return set_error(QCS_CUDA_ERR_INVALID, "swap_store must be bulk|thread, got '%s'", v.c_str());
   v = option_value("tile_bits");
   if (!v.empty()) o.tile_bits = std::atoi(v.c_str());
   if (o.tile_bits < QCS_MIN_TILE_BITS || o.tile_bits > QCS_TILE_BITS) o.tile_bits = Options().tile_bits;
@@ -230,6 +236,20 @@ static void fold_events(Engine &e) {
   e.pending_xchg_events.clear();
 }
 
+// ------------------------------------------------------------------ lazy |0...0>
+// q_state_init zeroes the vector and sets amplitude 0 (reference src/q_state.c:93-99).  That is 16
+// bytes written per amplitude which the first pass would read straight back, so qc_create only
+// NOTES that the state is |0...0>; whoever needs the bytes in memory calls this first.
+static int materialize(Engine &e) {
+  if (!e.zero_ket_pending) return QCS_CUDA_OK;
+  e.zero_ket_pending = false;
+  if (e.opt.dryrun) return QCS_CUDA_OK;
+  const bool owns_zero = !dist().active || dist().rank == 0;
+  CK(launch_init_state(e.live, e.local_size, owns_zero, e.stream));
+  e.kernel_launches++;
+  return QCS_CUDA_OK;
+}
+
 // ------------------------------------------------------------------ scratch buffer
 static int ensure_scratch(Engine &e) {
   if (e.scratch || e.opt.dryrun) return QCS_CUDA_OK;
@@ -319,23 +339,36 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
       ev1 = get_event(e);
       cudaEventRecord(ev0, e.stream);
     }
+    uint32_t pass_flags = 0;
+    if (e.zero_ket_pending) {
+      if (e.opt.tile_kernel == 0 || e.opt.tile_kernel == 3) {
+        pass_flags = QCS_PASS_SYNTH_ZERO_KET;  // this pass makes its own input
+        e.zero_ket_pending = false;
+      } else {
+        RC(materialize(e));  // the TMA-staged kernels always read
+      }
+    }
     if (!e.opt.dryrun) {
       if (carries) {
         SwapStore sw = *swap;
         sw.lpos_in_tile = 0;
         for (int pos : p.tile_positions)
           if ((uint32_t)pos == sw.lpos) sw.lpos_in_tile = 1;
-        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, &sw, e.opt.fast_math));
+        sw.bulk = e.opt.swap_bulk ? 1u : 0u;
+        sw.row_bits = 0;
+        while (sw.row_bits < (uint32_t)p.params.tile_bits && p.params.tile_pos[sw.row_bits] == sw.row_bits) sw.row_bits++;
+        sw.lpos_tile_bit = (uint32_t)__builtin_popcountll(p.params.nontile_mask & ((1ull << sw.lpos) - 1ull));
+        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, &sw, e.opt.fast_math, pass_flags));
         RC(dist_after_fused_swap(e));
       } else {
-        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, nullptr, e.opt.fast_math));
+        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, nullptr, e.opt.fast_math, pass_flags));
       }
     }
     e.passes++;
     e.kernel_launches++;
     e.segments += p.params.n_segments;
     e.gates_executed += p.params.n_gates - p.n_fan_headers;
-    const double bytes = 32.0 * (double)e.local_size;
+    const double bytes = (pass_flags & QCS_PASS_SYNTH_ZERO_KET ? 16.0 : 32.0) * (double)e.local_size;
     e.algorithmic_bytes += bytes;
     e.pass_bytes += bytes;
     e.pass_flops_per_amp += p.flops_per_amp;
@@ -363,6 +396,7 @@ static int run_local(Engine &e, const std::vector<PhysGate> &gates) {
     std::vector<PassPlan> plan = plan_batch(e, gates);
     RC(launch_passes(e, plan, 0, plan.size(), nullptr));
   } else {
+    RC(materialize(e));
     for (const PhysGate &g : gates) {
       if (g.c.kind == GK_NOP) continue;
       DGate dg;
@@ -440,6 +474,7 @@ static void note_swap(Engine &e, int lpos, int gpos) {
 }
 
 static int swap_positions(Engine &e, int lpos, int gpos) {
+  RC(materialize(e));
   if (!e.opt.dryrun) RC(dist_swap_positions(e, lpos, gpos));
   note_swap(e, lpos, gpos);
   if (e.opt.dryrun) {  // plan-only engines list stand-alone swaps between the passes (qcs_cuda_last_plan_swap)
@@ -655,6 +690,8 @@ static int flush(Engine &e) {
   if (e.poisoned)
     return set_error(QCS_CUDA_ERR_CUDA, "engine unusable after an earlier failure: %s", e.poison_reason.c_str());
   int rc = flush_queue(e);
+  // every call that reads or edits the amplitudes flushes first: from here on they are in memory
+  if (rc == QCS_CUDA_OK) rc = materialize(e);
   if (rc == QCS_CUDA_OK && e.swap_status_pending) {
     rc = check_cuda(cudaStreamSynchronize(e.stream), "cudaStreamSynchronize");
     if (rc == QCS_CUDA_OK) rc = dist_check_fused_swaps(e);
@@ -686,6 +723,7 @@ static int flush_queue(Engine &e) {
     RC(run_range(e, q, 0, q.size() - 1));
     if (dist().active) RC(canonicalize(e));  // the snapshot is taken in the identity layout
     RC(ensure_scratch(e));
+    RC(materialize(e));
     if (!e.opt.dryrun) {
       CK(cudaMemcpyAsync(e.scratch, e.live, e.local_size * sizeof(double2),
                          cudaMemcpyDeviceToDevice, e.stream));
@@ -700,6 +738,7 @@ static int flush_queue(Engine &e) {
 // Trades two LOCAL positions (a bit permutation of the shard, no communication).
 static int swap_local_positions(Engine &e, int a, int b) {
   if (a == b) return QCS_CUDA_OK;
+  RC(materialize(e));
   if (!e.opt.dryrun) {
     CK(launch_swap_local_bits(e.live, e.nl, a, b, e.stream));
     e.kernel_launches++;
@@ -968,11 +1007,9 @@ int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
   }
   if ((rc = check_cuda(cudaMemsetAsync(ws.result, 0, RES_COUNT * sizeof(double), e->stream), "cudaMemset")))
     return fail(rc);
-  // zero everything, amplitude 0 := 1 (reference src/q_state.c:93-99)
-  const bool owns_zero = !d.active || d.rank == 0;
-  if ((rc = check_cuda(launch_init_state(e->live, e->local_size, owns_zero, e->stream), "init_state")))
-    return fail(rc);
-  e->kernel_launches++;
+  // zero everything, amplitude 0 := 1 (reference src/q_state.c:93-99) -- lazily, see materialize()
+  e->zero_ket_pending = true;
+  if (!e->opt.lazy_init && (rc = materialize(*e))) return fail(rc);
   if ((rc = check_cuda(cudaStreamSynchronize(e->stream), "init sync"))) return fail(rc);
   if (d.active && e->opt.exchange == 1 && (rc = dist_open_peers(*e))) return fail(rc);
   *out = e;

@@ -35,6 +35,9 @@ struct Options {
   int reorder_segments = 8;
   bool peephole = true;    // drop exactly self-cancelling gate pairs from the queue (corrected semantics)
   bool fuse_swaps = true;  // fold position swaps into the stores of a pass (peer-memory path only)
+  bool lazy_init = true;   // qc_create writes nothing; see Engine::zero_ket_pending
+  bool swap_bulk = true;   // such a pass hands the amplitudes that leave to TMA bulk stores (row-sized NVLink
+                           // writes out of shared memory) instead of 16-byte st.global from the compute threads
   int tile_kernel = 3;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8), 3: ldg8 (512 thr x 8 amps, plain loads; default)
 };
 
@@ -70,6 +73,10 @@ struct Engine {
   bool poisoned = false;                  // a failed flush / swap left the amplitudes undefined: every later
                                           // call that needs them returns the error
   std::string poison_reason;
+  bool zero_ket_pending = false;   // `live` has not been written since qc_create: the state is |0...0> by
+                                   // definition.  The first fused pass synthesises its input (kernels.h
+                                   // QCS_PASS_SYNTH_ZERO_KET); anything else that looks at `live` first
+                                   // writes the state out (materialize, engine.cu)
   bool carried_sum_valid = false;  // ws.result[RES_LOCAL_SUM_*] holds the sum of this shard's amplitudes
   ReduceWorkspace ws{};
   void *ws_slab = nullptr;       // one allocation backing every array of ws

@@ -329,25 +329,16 @@ def emit(R, fast=False):
                  "neg.s32 low, wm;", "and.b32 low, low, wm;", "xor.b32 wm, wm, low;",
                  "and.b32 tst, mask, low;", "setp.eq.u32 pa, tst, 0;", f"@pa bra FS{n};"]
         body += entry
-        body += [f"FS{n}:", f"bra FL{n};"]
-        # Warp-uniform walk, software-pipelined: the phase of the NEXT entry is fetched (into the other
-        # register pair) before the FP64 block of the current one, so the constant load's latency hides
-        # behind 24-48 FP64 instructions of the same warp instead of stalling its first DMUL (ncu source
-        # view, profiles/r1u: the first DMUL after each LDCU pair carried 8 % of the pass's stall samples).
-        def fetch(pred, xr, xi):  # isolate the lowest pending entry, fetch its phase; all under `pred`
-            g = f"@{pred} " if pred else ""
-            return [f"{g}neg.s32 low, wm;", f"{g}and.b32 low, low, wm;", f"{g}xor.b32 wm, wm, low;",
-                    f"{g}bfind.u32 kidx, low;", f"{g}mul.wide.u32 ea, kidx, {E};", f"{g}add.u64 ea, ea, %1;",
-                    f"{g}ld.param.v2.f64 {{{xr}, {xi}}}, [ea+{E + OFF_M(6)}];"]
-        body += [f"FU{n}:", "setp.eq.u32 p, wm, 0;", f"@p bra FE{n};"]
-        body += fetch("", "dr", "di")
-        body += [f"FV{n}:", "setp.ne.u32 p, wm, 0;"] + fetch("p", "ar", "ai")
-        for r in diag_regs:
-            body += op_diag(r, "dr", "di")
-        body += [f"@!p bra FE{n};", "setp.ne.u32 p, wm, 0;"] + fetch("p", "dr", "di")
-        for r in diag_regs:
-            body += op_diag(r, "ar", "ai")
-        body += [f"@p bra.uni FV{n};",
+        body += [f"FS{n}:", f"bra FL{n};",
+                 f"FU{n}:", "setp.eq.u32 p, wm, 0;", f"@p bra FE{n};",
+                 "neg.s32 low, wm;", "and.b32 low, low, wm;", "xor.b32 wm, wm, low;"]
+        body += entry
+        # (Round 2: this loop was also tried software-pipelined -- the next entry's phase fetched into a
+        # second register pair before the current entry's FP64 block, two entries per trip.  The ncu source
+        # view had put 8 % of a QFT pass's stall samples on the first DMUL behind each LDCU pair, yet the
+        # 30-qubit QFT went from 62.5 to 63.8 ms: the other seven warps of the scheduler already cover
+        # that latency, and the USEL / predicated uniform instructions the pipelining adds are not free.)
+        body += [f"bra.uni FU{n};",
                  f"FE{n}:", "add.s32 %0, %0, K;", "bra DONE;",
                  # controls at arbitrary positions: gather the mask from the entries' cpos bytes
                  f"FG{n}:", "mov.u32 mask, 0;", "mov.u32 kidx, 0;", "mov.u64 ea, %1;",

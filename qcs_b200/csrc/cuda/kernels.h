@@ -21,15 +21,24 @@ struct SwapStore {
   uint32_t lpos;              // local position traded for the partner-selecting rank bit
   uint32_t my_gbit;           // my value of that rank bit
   uint32_t lpos_in_tile;      // lpos is one of the pass's tile positions
+  uint32_t bulk;              // 1: tiles with data for the partner leave through shared memory and TMA bulk
+                              // stores (cp.async.bulk.global.shared::cta, one per contiguous row), so NVLink
+                              // writes are row-sized and drain off the SM's store path; 0: 16-byte st.global
+  uint32_t row_bits;          // low tile positions 0..row_bits-1 are contiguous: a row = 16 << row_bits bytes
+  uint32_t lpos_tile_bit;     // lpos outside the tile: which bit of the tile NUMBER it is (tiles that leave and
+                              // tiles that stay then alternate in launch order instead of coming in two halves)
   uint32_t *abort_flag;       // my own device word: set when a CTA gave up waiting for the partner (the tile
                               // is then NOT stored and the engine reports QCS_CUDA_ERR_CUDA); later CTAs bail out
   unsigned long long spin_limit;  // clock64 ticks a CTA waits for the partner's signal before giving up
 };
 // fast (ldg8 only): the fused-multiply-add interpreter; `params` must come from a planner run with
 // PlannerConfig::fast_math (fan entries carry product tables instead of single phases).
+// pass_flags (plain-load kernels only): QCS_PASS_SYNTH_ZERO_KET = do not read the shard, it is the
+// never-written |0...0> of qc_create (amplitude 0 of the whole register is 1, everything else 0).
+enum { QCS_PASS_SYNTH_ZERO_KET = 1 };
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
                               cudaStream_t stream, int variant, const SwapStore *swap = nullptr,
-                              bool fast = false);
+                              bool fast = false, uint32_t pass_flags = 0);
 
 // multiprocessor count of the current device (cached per device); grids are sized from it
 int device_sm_count();

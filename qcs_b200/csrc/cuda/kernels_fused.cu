@@ -366,28 +366,6 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 #undef QCS_WITH_LDG
 #undef QCS_FAST
 
-// How many tiles ahead a CTA prefetches into L2 (QCS_CUDA_PREFETCH; off by default).
-static uint32_t prefetch_distance() {
-  static int d = -1;
-  if (d < 0) {
-    const char *v = getenv("QCS_CUDA_PREFETCH");
-    d = v ? atoi(v) : 0;  // measured: prefetching ahead into L2 costs ~10 % (profiles/r1_fused_kernel_history.md)
-    if (d < 0) d = 0;
-  }
-  return (uint32_t)d;
-}
-
-// One-off start delay of the second resident CTA of each SM (QCS_CUDA_STAGGER_NS).
-static uint32_t stagger_ns() {
-  static int d = -1;
-  if (d < 0) {
-    const char *v = getenv("QCS_CUDA_STAGGER_NS");
-    d = v ? atoi(v) : 0;
-    if (d < 0) d = 0;
-  }
-  return (uint32_t)d;
-}
-
 static int tile_row_bits(const PassParams &p) {
   int b = 0;
   while (b < QCS_TILE_BITS && p.tile_pos[b] == b) b++;
@@ -396,7 +374,7 @@ static int tile_row_bits(const PassParams &p) {
 
 }  // namespace
 
-using LdgKernel = void (*)(double2 *, const PassParams, uint32_t, uint32_t, uint32_t, const SwapStore);
+using LdgKernel = void (*)(double2 *, const PassParams, uint32_t, const SwapStore);
 
 // [math=fast][16 amplitudes per thread][tile bits - 10]
 static LdgKernel ldg_kernel(bool fast, bool r4, int T) {
@@ -440,10 +418,11 @@ int device_sm_count() {
 }
 
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
-                              cudaStream_t stream, int variant, const SwapStore *swap, bool fast) {
+                              cudaStream_t stream, int variant, const SwapStore *swap, bool fast,
+                              uint32_t pass_flags) {
   if (variant < 0 || variant > 3) return cudaErrorInvalidValue;
   const bool ldg = variant == 0 || variant == 3;
-  if ((swap || fast) && !ldg) return cudaErrorInvalidValue;  // plain-load kernels only
+  if ((swap || fast || pass_flags) && !ldg) return cudaErrorInvalidValue;  // plain-load kernels only
   SwapStore sw{};
   if (swap) sw = *swap;
   const int T = params.tile_bits;
@@ -455,7 +434,6 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
   DeviceLaunchState *dls = device_launch_state(&e);
   if (!dls) return e;
   const int sm_count = dls->sm_count;
-  const uint32_t pf = prefetch_distance(), st = stagger_ns();
   if (ldg) {
     const bool r4 = variant == 0;
     // math=fast: the tile + one 16-byte factor per uniform fan behind it
@@ -467,7 +445,7 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
       if (e != cudaSuccess) return e;
       configured = true;
     }
-    k<<<n_tiles, 1u << (T - params.reg_bits), smem, stream>>>(state, params, pf, st, (uint32_t)sm_count, sw);
+    k<<<n_tiles, 1u << (T - params.reg_bits), smem, stream>>>(state, params, pass_flags, sw);
     return cudaGetLastError();
   }
   const size_t smem_tma = (size_t)kSlots * kTileBytes + 128;  // slots + barriers + tile origins

@@ -91,17 +91,19 @@ def main():
     for name, (n, script) in big.items():
         orc = po.Oracle(n, "corrected")
         po.replay(orc, script)
-        for fuse in ("on", "off"):
-            c = Circuit(n, semantics="corrected", fuse_swaps=fuse)
-            po.replay(c, script); c.flush(); st = c.stats()
-            first, count = c._shard()
-            got = c.state(); want = orc.state()[first:first + count]
-            check(np.all(got == want), f"{name}/fuse_swaps={fuse}: {int(np.sum(got != want))} shard amplitudes differ")
-            check((st["fused_remaps"] > 0) == (fuse == "on"), f"{name}/fuse_swaps={fuse}: fused_remaps={st['fused_remaps']}")
-            if rank == 0:
-                print(f"done {name}/fuse_swaps={fuse}: passes={st['passes']} remaps={st['remaps']} "
-                      f"fused={st['fused_remaps']}", flush=True)
-            c.close()
+        # swaps on the stores of a pass through TMA bulk stores (default) / 16-byte stores, or stand-alone
+        for fuse, store in (("on", "bulk"), ("on", "thread"), ("off", None)):
+            for tile_bits in ((10, 11, 12) if fuse == "on" else (11,)):
+                c = Circuit(n, semantics="corrected", fuse_swaps=fuse, swap_store=store, tile_bits=tile_bits)
+                po.replay(c, script); c.flush(); st = c.stats()
+                first, count = c._shard()
+                got = c.state(); want = orc.state()[first:first + count]
+                tag = f"{name}/fuse_swaps={fuse}/{store}/t{tile_bits}"
+                check(np.all(got == want), f"{tag}: {int(np.sum(got != want))} shard amplitudes differ")
+                check((st["fused_remaps"] > 0) == (fuse == "on"), f"{tag}: fused_remaps={st['fused_remaps']}")
+                if rank == 0:
+                    print(f"done {tag}: passes={st['passes']} remaps={st['remaps']} fused={st['fused_remaps']}", flush=True)
+                c.close()
         # the same circuit in math=fast: whole-queue reordered schedule, swaps riding on its passes
         full = orc.state()
         for fuse in ("on", "off"):

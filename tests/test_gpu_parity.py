@@ -440,7 +440,7 @@ def test_single_header_bundle_runs_on_the_gpu(tmp_path):
     hdr = tmp_path / "qcs.h"
     subprocess.check_call([sys.executable, os.path.join(root, "scripts", "bundle.py"), str(hdr)])
     prog = tmp_path / "prog.c"
-    prog.write_text("""#define QCS_IMPLEMENTATION
+    prog.write_text(r"""#define QCS_IMPLEMENTATION
 #include "qcs.h"
 #include <stdio.h>
 #include <stdlib.h>
