@@ -97,6 +97,8 @@ static int load_options(Options &o) {
   else return set_error(QCS_CUDA_ERR_INVALID, "exchange must be p2p|nccl, got '%s'", v.c_str());
   v = option_value("fuse_swaps");
   o.fuse_swaps = !(v == "off" || v == "0");
+  v = option_value("fuse_argmax");
+  o.fuse_argmax = !(v == "off" || v == "0");
   v = option_value("lazy_init");
   o.lazy_init = !(v == "off" || v == "0");
   v = option_value("swap_store");
@@ -348,6 +350,14 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
         RC(materialize(e));  // the TMA-staged kernels always read
       }
     }
+    PassExtras extras{};
+    if (e.argmax_request && k + 1 == last && !swap && !e.opt.dryrun) {
+      pass_flags |= QCS_PASS_ARGMAX;
+      extras.argmax_p = e.argmax_tile_p;
+      extras.argmax_idx = e.argmax_tile_idx;
+      e.argmax_done = true;
+      e.argmax_tiles = e.local_size >> p.params.tile_bits;
+    }
     if (!e.opt.dryrun) {
       if (carries) {
         SwapStore sw = *swap;
@@ -361,7 +371,7 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
         CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, &sw, e.opt.fast_math, pass_flags));
         RC(dist_after_fused_swap(e));
       } else {
-        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, nullptr, e.opt.fast_math, pass_flags));
+        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, nullptr, e.opt.fast_math, pass_flags, &extras));
       }
     }
     e.passes++;
@@ -1037,6 +1047,8 @@ void qcs_cuda_state_destroy(qcs_cuda_engine *e) {
   pool_free(e->ws_slab, e->ws_slab_bytes);
   cudaFree(e->u_dev);
   cudaFree(e->idx_dev);
+  pool_free(e->argmax_tile_p, (e->local_size >> QCS_MIN_TILE_BITS) * sizeof(double));
+  pool_free(e->argmax_tile_idx, (e->local_size >> QCS_MIN_TILE_BITS) * sizeof(long long));
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1285,10 +1297,34 @@ int qcs_cuda_probability(qcs_cuda_engine *e, long index, double *p) {
 
 int qcs_cuda_argmax(qcs_cuda_engine *e, long *index) {
   if (!e || !index) return set_error(QCS_CUDA_ERR_INVALID, "null argument");
-  RC(flush(*e));
+  // Gates still queued on a single-GPU engine: the flush's last pass can do the first level of the
+  // reduction while the amplitudes are in registers (one candidate per tile), saving a 16-byte-per-
+  // amplitude sweep.  In-order plans only (one launch group, its last pass is the last word on every
+  // amplitude); same values, same tie rule as the stand-alone kernels.
+  e->argmax_request = e->argmax_done = false;
+  if (!e->queue.empty() && !dist().active && !e->opt.dryrun && e->opt.fuse_argmax && e->opt.fusion &&
+      e->opt.sem == SEM_CORRECTED && (e->opt.tile_kernel == 0 || e->opt.tile_kernel == 3) &&
+      e->nl >= min_tile_bits(*e) && !e->poisoned) {
+    const size_t n = (size_t)(e->local_size >> QCS_MIN_TILE_BITS);
+    if (!e->argmax_tile_p) {
+      if (pool_alloc((void **)&e->argmax_tile_p, n * sizeof(double)) != cudaSuccess) e->argmax_tile_p = nullptr;
+      if (e->argmax_tile_p && pool_alloc((void **)&e->argmax_tile_idx, n * sizeof(long long)) != cudaSuccess) {
+        pool_free(e->argmax_tile_p, n * sizeof(double));
+        e->argmax_tile_p = nullptr;
+      }
+      cudaGetLastError();
+    }
+    e->argmax_request = e->argmax_tile_p != nullptr;
+  }
+  const int flush_rc = flush(*e);
+  const bool fused = e->argmax_request && e->argmax_done;
+  e->argmax_request = e->argmax_done = false;
+  RC(flush_rc);
   RC(require_data(*e));
   const bool permuted = !layout_is_identity(*e);
-  if (permuted) {
+  if (fused) {
+    CK(launch_argmax_pairs(e->argmax_tile_p, e->argmax_tile_idx, e->argmax_tiles, e->ws, e->stream));
+  } else if (permuted) {
     // ties are decided by logical index inside the kernel: no need to restore the layout
     LogicalIndexLut lut;
     std::memset(&lut, 0, sizeof(lut));
@@ -1308,12 +1344,12 @@ int qcs_cuda_argmax(qcs_cuda_engine *e, long *index) {
     CK(launch_argmax(e->live, e->local_size, e->ws, e->stream));
   }
   e->kernel_launches += 2;
-  e->algorithmic_bytes += 16.0 * (double)e->local_size;
+  if (!fused) e->algorithmic_bytes += 16.0 * (double)e->local_size;
   struct { double p; long long idx; } mine{0.0, 0};
   CK(cudaMemcpyAsync(&mine.p, e->ws.result, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaMemcpyAsync(&mine.idx, e->ws.iresult, sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  if (!permuted) mine.idx += (long long)e->shard_base;
+  if (!permuted && !fused) mine.idx += (long long)e->shard_base;
   if (dist().active) {
     std::vector<decltype(mine)> all(dist().world);
     RC(dist_allgather_host(&mine, all.data(), sizeof(mine)));

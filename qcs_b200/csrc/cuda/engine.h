@@ -35,6 +35,7 @@ struct Options {
   int reorder_segments = 8;
   bool peephole = true;    // drop exactly self-cancelling gate pairs from the queue (corrected semantics)
   bool fuse_swaps = true;  // fold position swaps into the stores of a pass (peer-memory path only)
+  bool fuse_argmax = true; // qc_find_most_likely_state folds its first reduction level into the pass it flushes
   bool lazy_init = true;   // qc_create writes nothing; see Engine::zero_ket_pending
   bool swap_bulk = true;   // such a pass hands the amplitudes that leave to TMA bulk stores (row-sized NVLink
                            // writes out of shared memory) instead of 16-byte st.global from the compute threads
@@ -77,6 +78,13 @@ struct Engine {
                                    // definition.  The first fused pass synthesises its input (kernels.h
                                    // QCS_PASS_SYNTH_ZERO_KET); anything else that looks at `live` first
                                    // writes the state out (materialize, engine.cu)
+  // qc_find_most_likely_state right behind a run of gates: the last pass of the flush it triggers also
+  // leaves one (max |a|^2, index) candidate per tile (kernels.h QCS_PASS_ARGMAX)
+  bool argmax_request = false;     // set by qcs_cuda_argmax around its flush
+  bool argmax_done = false;        // the flush's last pass wrote argmax_tiles candidates
+  uint64_t argmax_tiles = 0;
+  double *argmax_tile_p = nullptr;       // device, one per tile of the smallest tile size
+  long long *argmax_tile_idx = nullptr;
   bool carried_sum_valid = false;  // ws.result[RES_LOCAL_SUM_*] holds the sum of this shard's amplitudes
   ReduceWorkspace ws{};
   void *ws_slab = nullptr;       // one allocation backing every array of ws

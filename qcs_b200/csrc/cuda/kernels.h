@@ -35,10 +35,17 @@ struct SwapStore {
 // PlannerConfig::fast_math (fan entries carry product tables instead of single phases).
 // pass_flags (plain-load kernels only): QCS_PASS_SYNTH_ZERO_KET = do not read the shard, it is the
 // never-written |0...0> of qc_create (amplitude 0 of the whole register is 1, everything else 0).
-enum { QCS_PASS_SYNTH_ZERO_KET = 1 };
+//   QCS_PASS_ARGMAX = every CTA also leaves (max |a|^2, lowest index holding it) of the tile it wrote in
+//   extras->argmax_p / argmax_idx [block index]: qc_find_most_likely_state right behind a run of gates
+//   then reduces 2^(nl-T) pairs (launch_argmax_pairs) instead of sweeping the shard once more.
+enum { QCS_PASS_SYNTH_ZERO_KET = 1, QCS_PASS_ARGMAX = 2 };
+struct PassExtras {
+  double *argmax_p;
+  long long *argmax_idx;
+};
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
                               cudaStream_t stream, int variant, const SwapStore *swap = nullptr,
-                              bool fast = false, uint32_t pass_flags = 0);
+                              bool fast = false, uint32_t pass_flags = 0, const PassExtras *extras = nullptr);
 
 // multiprocessor count of the current device (cached per device); grids are sized from it
 int device_sm_count();
@@ -97,6 +104,9 @@ cudaError_t launch_negate_one(double2 *dst, const double2 *src, uint64_t index,
                               double *carried_sum, cudaStream_t s);
 cudaError_t launch_argmax(const double2 *state, uint64_t n_amps, ReduceWorkspace &ws,
                           cudaStream_t s);  // result[0] = max prob, iresult[0] = first index
+// the same from n (probability, index) candidates (QCS_PASS_ARGMAX); ties go to the lowest index
+cudaError_t launch_argmax_pairs(const double *p, const long long *idx, uint64_t n, ReduceWorkspace &ws,
+                                cudaStream_t s);
 // Local (physical) index -> logical basis index under the current qubit layout, one table per index
 // byte (shards hold at most 2^32 amplitudes); `base` = the contribution of this rank's bits.
 struct LogicalIndexLut {

@@ -374,7 +374,7 @@ static int tile_row_bits(const PassParams &p) {
 
 }  // namespace
 
-using LdgKernel = void (*)(double2 *, const PassParams, uint32_t, const SwapStore);
+using LdgKernel = void (*)(double2 *, const PassParams, uint32_t, const SwapStore, const PassExtras);
 
 // [math=fast][16 amplitudes per thread][tile bits - 10]
 static LdgKernel ldg_kernel(bool fast, bool r4, int T) {
@@ -419,12 +419,15 @@ int device_sm_count() {
 
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
                               cudaStream_t stream, int variant, const SwapStore *swap, bool fast,
-                              uint32_t pass_flags) {
+                              uint32_t pass_flags, const PassExtras *extras) {
   if (variant < 0 || variant > 3) return cudaErrorInvalidValue;
   const bool ldg = variant == 0 || variant == 3;
   if ((swap || fast || pass_flags) && !ldg) return cudaErrorInvalidValue;  // plain-load kernels only
   SwapStore sw{};
   if (swap) sw = *swap;
+  PassExtras ex{};
+  if (extras) ex = *extras;
+  if ((pass_flags & QCS_PASS_ARGMAX) && (!ex.argmax_p || !ex.argmax_idx)) return cudaErrorInvalidValue;
   const int T = params.tile_bits;
   if (T < QCS_MIN_TILE_BITS || T > QCS_TILE_BITS || T > n_local) return cudaErrorInvalidValue;
   if (T != QCS_TILE_BITS && !ldg) return cudaErrorInvalidValue;  // the TMA kernels exist for 12-bit tiles only
@@ -445,7 +448,7 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
       if (e != cudaSuccess) return e;
       configured = true;
     }
-    k<<<n_tiles, 1u << (T - params.reg_bits), smem, stream>>>(state, params, pass_flags, sw);
+    k<<<n_tiles, 1u << (T - params.reg_bits), smem, stream>>>(state, params, pass_flags, sw, ex);
     return cudaGetLastError();
   }
   const size_t smem_tma = (size_t)kSlots * kTileBytes + 128;  // slots + barriers + tile origins

@@ -284,6 +284,32 @@ __global__ void __launch_bounds__(RB) argmax_kernel(const double2 *__restrict__ 
   }
 }
 
+// Second level of the argmax a fused pass started (QCS_PASS_ARGMAX): candidates instead of amplitudes.
+__global__ void __launch_bounds__(RB)
+argmax_pairs_kernel(const double *__restrict__ cand_p, const long long *__restrict__ cand_i, uint64_t n,
+                    double *partials, long long *ipartials) {
+  Best b{0.0, 0x7fffffffffffffffll};
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const Best c{cand_p[i], cand_i[i]};
+    if (c.p > 0.0) b = better(b, c);
+  }
+  __shared__ double shp[RB / 32];
+  __shared__ long long shi[RB / 32];
+  b = warp_best(b);
+  if ((threadIdx.x & 31) == 0) {
+    shp[threadIdx.x >> 5] = b.p;
+    shi[threadIdx.x >> 5] = b.idx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Best t{shp[0], shi[0]};
+    for (int w = 1; w < RB / 32; w++) t = better(t, Best{shp[w], shi[w]});
+    partials[blockIdx.x] = t.p;
+    ipartials[blockIdx.x] = t.idx;
+  }
+}
+
 // The same over a shard whose index bits are permuted (multi-GPU layouts after position swaps):
 // candidates are compared by their LOGICAL index, assembled from four byte-indexed tables
 // (LogicalIndexLut, built by the engine from the current layout), so "first maximum wins" holds
@@ -779,6 +805,14 @@ cudaError_t launch_negate_one(double2 *dst, const double2 *src, uint64_t index,
 cudaError_t launch_argmax(const double2 *state, uint64_t n, ReduceWorkspace &ws, cudaStream_t s) {
   const unsigned nb = grid_for(n, RB * 8);
   argmax_kernel<<<nb, RB, 0, s>>>(state, n, ws.partials, ws.ipartials);
+  argmax_final_kernel<<<1, 32, 0, s>>>(ws.partials, ws.ipartials, (int)nb, ws.result, ws.iresult);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_argmax_pairs(const double *p, const long long *idx, uint64_t n, ReduceWorkspace &ws,
+                                cudaStream_t s) {
+  const unsigned nb = grid_for(n, RB * 8);
+  argmax_pairs_kernel<<<nb, RB, 0, s>>>(p, idx, n, ws.partials, ws.ipartials);
   argmax_final_kernel<<<1, 32, 0, s>>>(ws.partials, ws.ipartials, (int)nb, ws.result, ws.iresult);
   return cudaGetLastError();
 }

@@ -476,3 +476,65 @@ int main(void) {
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.splitlines() == ["gates 3", "p0 0.500000 p7 0.500000 p1 0.000000", "shots 1000 ends 1000",
                                      "bv 22", "grover 1234 1"], r.stdout
+
+
+@pytest.mark.parametrize("tile_kernel,tile_bits", [("ldg8", 10), ("ldg8", 11), ("ldg8", 12), ("ldg", 11), ("tma", 12)])
+def test_lazy_zero_ket_equals_eager_init(tile_kernel, tile_bits):
+    """qc_create writes nothing (the first fused pass synthesises |0...0>, anything else materialises
+    it first): same bits as with the init kernel, for every way a fresh circuit can be touched first."""
+    n = 14
+    script = po.random_circuit_script(n, 3, seed=41) + [("qft",)]
+    zero = np.zeros(2 ** n, complex); zero[0] = 1.0
+    for lazy in ("on", "off"):
+        kw = dict(semantics="corrected", tile_kernel=tile_kernel, tile_bits=tile_bits, lazy_init=lazy)
+        c = Circuit(n, **kw); assert _same(c.state(), zero); c.close()               # read first
+        c = Circuit(n, **kw); assert c.get_probability(0) == 1.0 and c.find_most_likely_state() == 0; c.close()
+        c = Circuit(n, **kw); po.srand(3); assert c.measure(5) == 0 and _same(c.state(), zero); c.close()
+        c = Circuit(n, **kw); c.phase_flip(0); want = zero.copy(); want[0] = -1.0; assert _same(c.state(), want); c.close()
+        orc = po.Oracle(n, "corrected"); po.replay(orc, script)
+        c = Circuit(n, **kw); po.replay(c, script)                                     # fused pass first
+        assert _same(c.state(), orc.state()), lazy
+        c.close()
+        c = Circuit(n, fusion="off", **kw); po.replay(c, script)                      # per-gate kernels first
+        assert _same(c.state(), orc.state()), lazy
+        c.close(); orc.close()
+    c = Circuit(n, semantics="reference", lazy_init="on"); c.h(3)                      # one gate: snapshot of |0...0>
+    assert _same(c.scratch(), zero)
+    c.close()
+    a = Circuit(n, semantics="corrected", lazy_init="on"); a.h(0); a.flush()
+    b = Circuit(n, semantics="corrected", lazy_init="off"); b.h(0); b.flush()
+    assert a.stats()["kernel_launches"] == b.stats()["kernel_launches"] - 1
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("tile_bits", [10, 11, 12])
+@pytest.mark.parametrize("n", [10, 13, 17, 21])
+def test_argmax_fused_into_the_last_pass(n, tile_bits):
+    """qc_find_most_likely_state behind queued gates (reference src/qcs.c:464-478): one candidate per
+    tile from the flush's last pass.  Same answer as the stand-alone sweep and the oracle: first
+    maximum wins (ties!), strict >."""
+    if n < tile_bits:
+        pytest.skip("shard smaller than the tile")
+    rng = np.random.default_rng(600 + n)
+    scripts = {
+        "uniform_ties": [("h", q) for q in range(n)],                         # all equal: index 0
+        "two_maxima": [("x", n - 1), ("h", 0), ("h", n - 2)],                  # four equal maxima, lowest wins
+        "ghz": [("ghz",)],
+        "random": _random_script(rng, n, 80, generic=False),
+        "brickwork": po.random_circuit_script(n, 5, seed=n),
+        "basis": [("x", q) for q in range(n) if (0x2B5C7 >> q) & 1] + [("z", 1), ("rz", 3, 0.4)],
+        "qft_of_basis": [("x", 2), ("x", n - 1), ("qft",)],
+    }
+    for name, script in scripts.items():
+        orc = po.Oracle(n, "corrected"); po.replay(orc, script)
+        want = orc.find_most_likely_state()
+        got = {}
+        for fuse in ("on", "off"):
+            c = Circuit(n, semantics="corrected", tile_bits=tile_bits, fuse_argmax=fuse)
+            po.replay(c, script)
+            got[fuse] = c.find_most_likely_state()
+            assert c.find_most_likely_state() == got[fuse]        # second call: nothing queued, plain sweep
+            assert _same(c.state(), orc.state()), name
+            c.close()
+        assert got["on"] == got["off"] == want, (name, got, want)
+        orc.close()
