@@ -500,10 +500,10 @@ def main() -> None:
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(e2e_steps):
-        ce = Circuit(n, **kw)                      # qc_create: cudaMalloc + init kernel
-        ce.qft()                                   # 465 qc_h / qc_cphase calls
-        prob = ce.get_probability(12345)           # flush + D2H of one amplitude
-        best = ce.find_most_likely_state()         # device argmax + D2H
+        ce = Circuit(n, **kw)                      # qc_create: buffers from the pool; |0...0> is not written out
+        ce.qft()                                   # 465 qc_h / qc_cphase calls (queued)
+        best = ce.find_most_likely_state()         # flush: the fused passes, argmax candidates from the last one, D2H
+        prob = ce.get_probability(12345)           # D2H of one amplitude
         d2h += 16 + 16
         ce.close()                                 # qc_destroy
     barrier()
@@ -613,8 +613,8 @@ def main() -> None:
         },
         "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": h2d_per_step,
                 "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps,
-                "what": "qc_create + qc_quantum_fourier_transform + qc_get_probability + "
-                        "qc_find_most_likely_state + qc_destroy through libqcs.so"},
+                "what": "qc_create + qc_quantum_fourier_transform + qc_find_most_likely_state + "
+                        "qc_get_probability + qc_destroy through libqcs.so"},
         "gpu_launches": st["kernel_launches"],
         "clocks": clocks,
         "sanity": {"p(|0>) after the timed QFTs": p0, "sharded_parity": parity},

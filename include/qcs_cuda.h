@@ -143,6 +143,7 @@ typedef struct qcs_cuda_stats {
   double pass_flops_per_amp;   /* separately rounded FP64 operations per
                                   amplitude, summed over executed passes     */
   long gates_cancelled;        /* dropped by the queue peephole (exact pairs) */
+  long multi_remaps;           /* carrying passes that traded 2 or 3 position pairs at once (counted in fused_remaps) */
 } qcs_cuda_stats;
 
 int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out);
@@ -171,9 +172,10 @@ long qcs_cuda_describe_last_plan(qcs_cuda_engine *e, char *buf, long cap);
  * into buf (when cap is large enough); returns the number of passes of the last flush.  Lets a
  * CPU test interpret exactly what the GPU would be handed (tests/test_planner.py). */
 long qcs_cuda_last_plan_raw(qcs_cuda_engine *e, long pass_index, void *buf, long cap);
-/* Sharded engines: returns 1 and the two positions when entry `pass_index` of the last flush trades a
- * local position for a global one -- on the stores of that pass, or (plan-only engines list these
- * too, as entries with no segments) as a stand-alone swap between passes; 0 otherwise. */
+/* Sharded engines: how many (local position, global position) pairs entry `pass_index` of the last
+ * flush trades -- all at once on the stores of that pass (a remap of up to 3 pairs: an all-to-all
+ * among 2^k ranks), or (plan-only engines list these too, as entries with no segments) as a
+ * stand-alone swap between passes -- and which: lpos / gpos must hold 3 ints each.  0: none. */
 long qcs_cuda_last_plan_swap(qcs_cuda_engine *e, long pass_index, int *lpos, int *gpos);
 /* Per-pass figures of the last flush (timing enabled): device time in ms (-1 when not measured), the
  * planner's FP64 operation count per amplitude, tile bits and segment count of pass `pass_index`.

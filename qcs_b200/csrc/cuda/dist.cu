@@ -141,10 +141,13 @@ int dist_open_peers(Engine &e) {
   if (!d.active || e.opt.dryrun) return QCS_CUDA_OK;
   const size_t n_tiles = e.nl >= QCS_MIN_TILE_BITS ? (size_t)1 << (e.nl - QCS_MIN_TILE_BITS) : 0;
   if (n_tiles) {
-    // one word per tile + (behind them) the abort word of the bounded handshake wait
-    CK(cudaMalloc(&e.tile_flags, (n_tiles + 1) * sizeof(uint32_t)));
-    CK(cudaMemset(e.tile_flags, 0, (n_tiles + 1) * sizeof(uint32_t)));
-    e.swap_abort_flag = e.tile_flags + n_tiles;
+    // per sending rank of a remap group (<= 2^QCS_MAX_REMAP) one word per tile + (behind them) the
+    // abort word of the bounded handshake wait
+    const size_t words = (n_tiles << QCS_MAX_REMAP) + 1;
+    CK(cudaMalloc(&e.tile_flags, words * sizeof(uint32_t)));
+    CK(cudaMemset(e.tile_flags, 0, words * sizeof(uint32_t)));
+    e.tile_flag_stride = (uint32_t)n_tiles;
+    e.swap_abort_flag = e.tile_flags + (n_tiles << QCS_MAX_REMAP);
     if (!e.swap_status_host) CK(cudaMallocHost(&e.swap_status_host, sizeof(int)));
     *e.swap_status_host = 0;
   }
@@ -223,24 +226,33 @@ bool dist_p2p_available(const Engine &e) {
   return dist().active && e.opt.exchange == 1 && e.opt.sem == SEM_CORRECTED && !e.peer_live.empty();
 }
 
-// A position swap folded into the stores of a fused pass (kernels.h SwapStore): fills in the
-// partner's addresses.  False when the peer-memory path is not available.
-bool dist_fused_swap_args(Engine &e, int lpos, int gpos, SwapStore &sw) {
-  if (!dist_p2p_available(e) || !e.tile_flags) return false;
+// A remap of k position pairs folded into the stores of a fused pass (kernels.h SwapStore): fills in
+// the addresses of the 2^k ranks of the exchange.  False when the peer-memory path is not available.
+bool dist_fused_swap_args(Engine &e, int k, const int *lpos, const int *gpos, SwapStore &sw) {
+  if (!dist_p2p_available(e) || !e.tile_flags || k < 1 || k > QCS_MAX_REMAP) return false;
   DistContext &d = dist();
-  const int gbit = gpos - e.nl;
-  const int partner = d.rank ^ (1 << gbit);
-  if (!e.peer_flags[partner]) return false;
-  sw.peer = e.peer_live[partner];
+  std::memset(&sw, 0, sizeof(sw));
+  sw.k = (uint32_t)k;
+  for (int i = 0; i < k; i++) {
+    sw.lpos[i] = (uint32_t)lpos[i];
+    sw.my_gbits |= (uint32_t)((d.rank >> (gpos[i] - e.nl)) & 1) << i;
+  }
+  for (int b = 0; b < (1 << k); b++) {
+    int r = d.rank;
+    for (int i = 0; i < k; i++) {
+      const int gbit = gpos[i] - e.nl;
+      r = (r & ~(1 << gbit)) | (((b >> i) & 1) << gbit);
+    }
+    if (!e.peer_live[r] || !e.peer_flags[r]) return false;
+    sw.peer[b] = e.peer_live[r];
+    sw.peer_flags[b] = e.peer_flags[r] + (size_t)sw.my_gbits * e.tile_flag_stride;
+  }
   sw.my_flags = e.tile_flags;
-  sw.peer_flags = e.peer_flags[partner];
+  sw.flag_stride = e.tile_flag_stride;
   sw.epoch = ++e.swap_epoch;
-  sw.lpos = (uint32_t)lpos;
-  sw.my_gbit = (uint32_t)((d.rank >> gbit) & 1);
-  sw.lpos_in_tile = 0;  // the caller knows the pass's tile
   sw.abort_flag = e.swap_abort_flag;
   sw.spin_limit = swap_spin_limit();
-  return true;
+  return true;  // in_tile, n_out, out_pair, out_tile_bit, bulk, row_bits: the caller knows the pass's tile
 }
 
 // After a pass that stored into the partner's shard: nobody reads swapped data before both

@@ -97,6 +97,9 @@ static int load_options(Options &o) {
   else return set_error(QCS_CUDA_ERR_INVALID, "exchange must be p2p|nccl, got '%s'", v.c_str());
   v = option_value("fuse_swaps");
   o.fuse_swaps = !(v == "off" || v == "0");
+  v = option_value("remap_max");
+  if (!v.empty()) o.remap_max = std::atoi(v.c_str());
+  if (o.remap_max < 1 || o.remap_max > QCS_MAX_REMAP) o.remap_max = Options().remap_max;
   v = option_value("fuse_argmax");
   o.fuse_argmax = !(v == "off" || v == "0");
   v = option_value("lazy_init");
@@ -329,8 +332,10 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
 }
 
 // Launches planned passes [first, last); `swap` (may be null) rides on the stores of the last one.
+// (n_swaps position pairs swap_lpos[i] <-> swap_gpos[i]: dist_fused_swap_args filled in the ranks' addresses)
 static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t first, size_t last,
-                         const SwapStore *swap, int swap_lpos = -1, int swap_gpos = -1) {
+                         const SwapStore *swap, int n_swaps = 0, const int *swap_lpos = nullptr,
+                         const int *swap_gpos = nullptr) {
   const bool timed = e.timing && !e.opt.dryrun;
   for (size_t k = first; k < last; k++) {
     const PassPlan &p = plan[k];
@@ -361,13 +366,30 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
     if (!e.opt.dryrun) {
       if (carries) {
         SwapStore sw = *swap;
-        sw.lpos_in_tile = 0;
-        for (int pos : p.tile_positions)
-          if ((uint32_t)pos == sw.lpos) sw.lpos_in_tile = 1;
+        sw.in_tile = 0;
+        sw.n_out = 0;
+        for (uint32_t i = 0; i < sw.k; i++) {
+          bool in_tile = false;
+          for (int pos : p.tile_positions)
+            if ((uint32_t)pos == sw.lpos[i]) in_tile = true;
+          if (in_tile) {
+            sw.in_tile |= 1u << i;
+            continue;
+          }
+          // which bit of the tile NUMBER this position is; kept sorted ascending (kernels.h)
+          const uint32_t bit = (uint32_t)__builtin_popcountll(p.params.nontile_mask & ((1ull << sw.lpos[i]) - 1ull));
+          uint32_t j = sw.n_out++;
+          while (j > 0 && sw.out_tile_bit[j - 1] > bit) {
+            sw.out_tile_bit[j] = sw.out_tile_bit[j - 1];
+            sw.out_pair[j] = sw.out_pair[j - 1];
+            j--;
+          }
+          sw.out_tile_bit[j] = bit;
+          sw.out_pair[j] = i;
+        }
         sw.bulk = e.opt.swap_bulk ? 1u : 0u;
         sw.row_bits = 0;
         while (sw.row_bits < (uint32_t)p.params.tile_bits && p.params.tile_pos[sw.row_bits] == sw.row_bits) sw.row_bits++;
-        sw.lpos_tile_bit = (uint32_t)__builtin_popcountll(p.params.nontile_mask & ((1ull << sw.lpos) - 1ull));
         CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, &sw, e.opt.fast_math, pass_flags));
         RC(dist_after_fused_swap(e));
       } else {
@@ -384,8 +406,11 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
     e.pass_flops_per_amp += p.flops_per_amp;
     e.last_plan.push_back(p);
     if (carries) {
-      e.last_plan.back().swap_lpos = swap_lpos;
-      e.last_plan.back().swap_gpos = swap_gpos;
+      e.last_plan.back().n_swaps = n_swaps;
+      for (int i = 0; i < n_swaps && i < 3; i++) {
+        e.last_plan.back().swap_lpos[i] = swap_lpos[i];
+        e.last_plan.back().swap_gpos[i] = swap_gpos[i];
+      }
     }
     if (timed) {
       cudaEventRecord(ev1, e.stream);
@@ -436,34 +461,38 @@ static int run_local(Engine &e, const std::vector<PhysGate> &gates) {
 // the positions every tile contains can be paired in ANY later pass (QFT: the three incoming
 // qubits join the last pass instead of needing one of their own), at the price of 64..256-byte
 // instead of 512-byte remote store runs.
-static int pick_victim(const Engine &e, const std::vector<HostGate> &q, size_t from, size_t since,
-                       int lowest) {
-  std::vector<long> next_use(e.nl, (long)q.size() + 1), last_use(e.nl, -1);
+struct VictimRanking {
+  std::vector<int> order;       // local positions, best victim first
+  std::vector<long> next_use;   // per position (local AND global): queue index of the next pairing use at or
+                                // after `from` of the qubit sitting there, q.size() + 1 if none
+};
+static VictimRanking rank_victims(const Engine &e, const std::vector<HostGate> &q, size_t from, size_t since,
+                                  int lowest) {
+  VictimRanking vr;
+  vr.next_use.assign(e.n, (long)q.size() + 1);
+  std::vector<long> last_use(e.n, -1);
   for (size_t i = q.size(); i-- > since;) {
     Classified c = classify_gate(q[i].m, q[i].control >= 0, e.opt.sem);
     if (!is_pairing_kind(c.kind)) continue;
     int pos = e.perm[q[i].target];
-    if (pos >= e.nl) continue;
-    if (i >= from) next_use[pos] = (long)i;
+    if (i >= from) vr.next_use[pos] = (long)i;
     else if (last_use[pos] < 0) last_use[pos] = (long)i;
   }
-  int best = e.nl - 1;
-  long best_next = -1, best_last = 0;
-  bool best_low = false;
-  for (int pos = e.nl - 1; pos >= lowest && pos >= 0; pos--) {
-    // positions every tile contains (only offered when lowest < 5) win ties: whatever arrives there
-    // is pairable in every later pass
-    const bool low = pos < QCS_LANE_BITS;
-    if (next_use[pos] > best_next ||
-        (next_use[pos] == best_next &&
-         (last_use[pos] < best_last || (last_use[pos] == best_last && low && !best_low)))) {
-      best_next = next_use[pos];
-      best_last = last_use[pos];
-      best_low = low;
-      best = pos;
-    }
-  }
-  return best;
+  for (int pos = e.nl - 1; pos >= lowest && pos >= 0; pos--) vr.order.push_back(pos);
+  // farthest next use first; then the longest idle; then positions every tile contains (only offered
+  // when lowest < 5: whatever arrives there is pairable in every later pass); then the highest
+  std::stable_sort(vr.order.begin(), vr.order.end(), [&](int a, int b) {
+    if (vr.next_use[a] != vr.next_use[b]) return vr.next_use[a] > vr.next_use[b];
+    if (last_use[a] != last_use[b]) return last_use[a] < last_use[b];
+    return (a < QCS_LANE_BITS) && !(b < QCS_LANE_BITS);
+  });
+  if (vr.order.empty()) vr.order.push_back(e.nl - 1);
+  return vr;
+}
+
+static int pick_victim(const Engine &e, const std::vector<HostGate> &q, size_t from, size_t since,
+                       int lowest) {
+  return rank_victims(e, q, from, since, lowest).order[0];
 }
 
 static void note_swap(Engine &e, int lpos, int gpos) {
@@ -492,8 +521,9 @@ static int swap_positions(Engine &e, int lpos, int gpos) {
     std::memset(&marker.params, 0, sizeof(marker.params));
     marker.n_gates_api = 0;
     marker.flops_per_amp = 0.0;
-    marker.swap_lpos = lpos;
-    marker.swap_gpos = gpos;
+    marker.n_swaps = 1;
+    marker.swap_lpos[0] = lpos;
+    marker.swap_gpos[0] = gpos;
     e.last_plan.push_back(marker);
   }
   return QCS_CUDA_OK;
@@ -557,7 +587,7 @@ static int run_range_reordered(Engine &e, const std::vector<HostGate> &q, size_t
           chosen = k;
     }
     SwapStore sw{};
-    const bool ride = fuse && !plan.empty() && (e.opt.dryrun || dist_fused_swap_args(e, victim, gpos, sw));
+    const bool ride = fuse && !plan.empty() && (e.opt.dryrun || dist_fused_swap_args(e, 1, &victim, &gpos, sw));
     const size_t n_run = plan.empty() ? 0 : (ride ? chosen + 1 : plan.size());
     std::vector<char> ran(pend.size(), 0);
     std::vector<PhysGate> ran_gates;
@@ -568,7 +598,7 @@ static int run_range_reordered(Engine &e, const std::vector<HostGate> &q, size_t
       }
     if (e.opt.dryrun) trace_gates(e, ran_gates);
     if (ride) {
-      RC(launch_passes(e, plan, 0, n_run, &sw, victim, gpos));
+      RC(launch_passes(e, plan, 0, n_run, &sw, 1, &victim, &gpos));
       note_swap(e, victim, gpos);
       e.fused_swaps++;
     } else {
@@ -597,17 +627,45 @@ static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, si
     }
     if (x == end) return run_local(e, batch);
     const int gpos = e.perm[q[x].target];
-    const int victim = pick_victim(e, q, x, i, fuse ? e.opt.min_fused_victim : QCS_LANE_BITS);
+    const VictimRanking vr = rank_victims(e, q, x, i, fuse ? e.opt.min_fused_victim : QCS_LANE_BITS);
+    const int victim = vr.order[0];
     if (!fuse) {
       RC(run_local(e, batch));
       RC(swap_positions(e, victim, gpos));
       i = x;
       continue;
     }
-    // the swap may happen anywhere after the last pairing gate on the victim position
+    // Remap of k positions at once: the pass that carries this swap can bring in
+    // OTHER global-resident qubits too -- an all-to-all among 2^k ranks moves (1 - 2^-k) of the shard
+    // where k separate swaps move k halves, and costs one carrying pass instead of k.  A qubit joins
+    // when it will be paired before the victim it displaces would be (evicting that victim now
+    // instead of then loses nothing); candidates in order of urgency, victims in order of idleness.
+    int lpos_k[QCS_MAX_REMAP] = {victim, -1, -1}, gpos_k[QCS_MAX_REMAP] = {gpos, -1, -1};
+    int k_pairs = 1;
+    {
+      std::vector<int> others;
+      for (int g = e.nl; g < e.n; g++)
+        if (g != gpos) others.push_back(g);
+      std::sort(others.begin(), others.end(), [&](int a, int b) { return vr.next_use[a] < vr.next_use[b]; });
+      const int kmax = std::min(std::min(e.opt.remap_max, QCS_MAX_REMAP), e.n - e.nl);
+      size_t vi = 1;
+      for (int g : others) {
+        if (k_pairs >= kmax || vi >= vr.order.size()) break;
+        const int v = vr.order[vi];
+        if (vr.next_use[g] < vr.next_use[v]) {
+          lpos_k[k_pairs] = v;
+          gpos_k[k_pairs] = g;
+          k_pairs++;
+          vi++;
+        }
+      }
+    }
+    // the remap may happen anywhere after the last pairing gate on a victim position
     size_t legal_from = i;
     for (size_t k = i; k < x; k++)
-      if (is_pairing_kind(batch[k - i].c.kind) && batch[k - i].tpos == victim) legal_from = k + 1;
+      if (is_pairing_kind(batch[k - i].c.kind))
+        for (int j = 0; j < k_pairs; j++)
+          if (batch[k - i].tpos == lpos_k[j]) legal_from = k + 1;
     std::vector<PassPlan> plan = plan_batch(e, batch);
     size_t pass_end = i, chosen = plan.size();
     for (size_t k = 0; k < plan.size(); k++) {
@@ -624,16 +682,19 @@ static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, si
       continue;
     }
     SwapStore sw{};
-    if (!e.opt.dryrun && !dist_fused_swap_args(e, victim, gpos, sw)) {
+    if (!e.opt.dryrun && !dist_fused_swap_args(e, k_pairs, lpos_k, gpos_k, sw)) {
       RC(run_local(e, batch));
       RC(swap_positions(e, victim, gpos));
       i = x;
       continue;
     }
     if (e.opt.dryrun) trace_gates(e, std::vector<PhysGate>(batch.begin(), batch.begin() + (long)(pass_end - i)));
-    RC(launch_passes(e, plan, 0, chosen + 1, &sw, victim, gpos));
-    note_swap(e, victim, gpos);
+    RC(launch_passes(e, plan, 0, chosen + 1, &sw, k_pairs, lpos_k, gpos_k));
+    for (int j = 0; j < k_pairs; j++) note_swap(e, lpos_k[j], gpos_k[j]);
+    // bytes that crossed NVLink per direction: (1 - 2^-k) of the shard, not k halves
+    e.exchange_bytes += (16.0 * (1.0 - std::ldexp(1.0, -k_pairs)) - 8.0 * k_pairs) * (double)e.local_size;
     e.fused_swaps++;
+    if (k_pairs > 1) e.multi_remaps++;
     i = pass_end;  // the rest of the batch is planned again under the new layout
   }
   return QCS_CUDA_OK;
@@ -1418,6 +1479,7 @@ int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out) {
   out->fused_remap_pass_ms = e->fused_swap_pass_ms;
   out->pass_flops_per_amp = e->pass_flops_per_amp;
   out->gates_cancelled = e->gates_cancelled;
+  out->multi_remaps = e->multi_remaps;
   return QCS_CUDA_OK;
 }
 
@@ -1427,6 +1489,7 @@ int qcs_cuda_reset_stats(qcs_cuda_engine *e) {
   e->gates_submitted = e->gates_executed = e->passes = e->kernel_launches = e->segments = e->remaps = 0;
   e->algorithmic_bytes = e->pass_bytes = e->pass_ms = e->exchange_bytes = e->exchange_ms = 0;
   e->fused_swaps = 0;
+  e->multi_remaps = 0;
   e->gates_cancelled = 0;
   e->fused_swap_pass_ms = 0;
   e->pass_flops_per_amp = 0;
@@ -1505,10 +1568,11 @@ long qcs_cuda_describe_last_plan(qcs_cuda_engine *e, char *buf, long cap) {
 long qcs_cuda_last_plan_swap(qcs_cuda_engine *e, long pass_index, int *lpos, int *gpos) {
   if (!e || pass_index < 0 || pass_index >= (long)e->last_plan.size()) return 0;
   const PassPlan &p = e->last_plan[(size_t)pass_index];
-  if (p.swap_lpos < 0) return 0;
-  if (lpos) *lpos = p.swap_lpos;
-  if (gpos) *gpos = p.swap_gpos;
-  return 1;
+  for (int i = 0; i < p.n_swaps && i < 3; i++) {
+    if (lpos) lpos[i] = p.swap_lpos[i];
+    if (gpos) gpos[i] = p.swap_gpos[i];
+  }
+  return p.n_swaps;
 }
 
 long qcs_cuda_last_plan_pass_info(qcs_cuda_engine *e, long pass_index, double *ms, double *flops_per_amp,

@@ -35,6 +35,7 @@ struct Options {
   int reorder_segments = 8;
   bool peephole = true;    // drop exactly self-cancelling gate pairs from the queue (corrected semantics)
   bool fuse_swaps = true;  // fold position swaps into the stores of a pass (peer-memory path only)
+  int remap_max = 3;       // position pairs one carrying pass may trade (1..3): an all-to-all among 2^k ranks
   bool fuse_argmax = true; // qc_find_most_likely_state folds its first reduction level into the pass it flushes
   bool lazy_init = true;   // qc_create writes nothing; see Engine::zero_ket_pending
   bool swap_bulk = true;   // such a pass hands the amplitudes that leave to TMA bulk stores (row-sized NVLink
@@ -68,6 +69,7 @@ struct Engine {
   uint32_t *tile_flags = nullptr;         // one word per tile: handshake of passes that swap on the way out
   std::vector<uint32_t *> peer_flags;     // every rank's tile_flags, peer-mapped
   uint32_t swap_epoch = 0;
+  uint32_t tile_flag_stride = 0;          // words per sending rank in tile_flags
   uint32_t *swap_abort_flag = nullptr;    // device word behind tile_flags: a CTA gave up waiting for its partner
   int *swap_status_host = nullptr;        // pinned: all-reduced abort words of the last swap-carrying pass
   bool swap_status_pending = false;       // a status copy is in flight on the stream
@@ -106,6 +108,7 @@ struct Engine {
   long long gates_submitted = 0, gates_executed = 0, passes = 0, kernel_launches = 0,
             segments = 0, remaps = 0;
   long long gates_cancelled = 0;  // dropped by the queue peephole
+  long long multi_remaps = 0;  // carrying passes that traded more than one position pair
   long long fused_swaps = 0;   // remaps that rode on a pass instead of getting a kernel of their own
   double algorithmic_bytes = 0, pass_bytes = 0, pass_ms = 0, exchange_bytes = 0, exchange_ms = 0;
   double pass_flops_per_amp = 0;  // planner's FP64 operation count per amplitude, summed over executed passes
@@ -137,7 +140,7 @@ int dist_barrier(Engine &e);
 int dist_open_peers(Engine &e);
 bool dist_p2p_available(const Engine &e);
 int dist_p2p_swap(Engine &e, cudaStream_t stream, int lpos, int gpos);
-bool dist_fused_swap_args(Engine &e, int lpos, int gpos, SwapStore &sw);
+bool dist_fused_swap_args(Engine &e, int k, const int *lpos, const int *gpos, SwapStore &sw);
 int dist_after_fused_swap(Engine &e);
 int dist_check_fused_swaps(Engine &e);  // after a stream synchronisation: error if a handshake wait timed out
 void dist_close_peers(Engine &e);

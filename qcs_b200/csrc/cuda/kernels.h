@@ -10,26 +10,37 @@ namespace qcs {
 // kernels_fused.cu ----------------------------------------------------------
 // variant 0: one CTA per tile, plain 128-bit global loads/stores
 // variant 1: persistent CTAs, tiles staged through shared memory by TMA bulk copies
-// swap (ldg variants only, multi-GPU): the pass also performs a position swap with the partner rank
-// on its way out -- see SwapStore.
+// swap (plain-load kernels only, multi-GPU): the pass also trades up to QCS_MAX_REMAP local positions
+// for global ones on its way out -- an all-to-all among the 2^k ranks that differ in the traded rank
+// bits.  An amplitude whose bits at the traded local positions are b = (b_0 .. b_k-1) lands in the
+// shard of the rank whose traded rank bits are b (the other rank bits are mine), at its own index
+// with those local bits replaced by MY traded rank bits; (1 - 2^-k) of the shard crosses NVLink,
+// against k halves for k separate swaps.
+#define QCS_MAX_REMAP 3
 struct SwapStore {
-  double2 *peer;              // partner's state buffer (peer-mapped); nullptr = plain pass
-  const uint32_t *my_flags;   // one word per tile: the partner's CTA writes `epoch` once it has loaded
-                              // the tile my results will overwrite
-  uint32_t *peer_flags;       // the partner's flag array (peer-mapped)
-  uint32_t epoch;             // value of this pass (strictly increasing per engine)
-  uint32_t lpos;              // local position traded for the partner-selecting rank bit
-  uint32_t my_gbit;           // my value of that rank bit
-  uint32_t lpos_in_tile;      // lpos is one of the pass's tile positions
-  uint32_t bulk;              // 1: tiles with data for the partner leave through shared memory and TMA bulk
-                              // stores (cp.async.bulk.global.shared::cta, one per contiguous row), so NVLink
-                              // writes are row-sized and drain off the SM's store path; 0: 16-byte st.global
-  uint32_t row_bits;          // low tile positions 0..row_bits-1 are contiguous: a row = 16 << row_bits bytes
-  uint32_t lpos_tile_bit;     // lpos outside the tile: which bit of the tile NUMBER it is (tiles that leave and
-                              // tiles that stay then alternate in launch order instead of coming in two halves)
-  uint32_t *abort_flag;       // my own device word: set when a CTA gave up waiting for the partner (the tile
-                              // is then NOT stored and the engine reports QCS_CUDA_ERR_CUDA); later CTAs bail out
-  unsigned long long spin_limit;  // clock64 ticks a CTA waits for the partner's signal before giving up
+  uint32_t k;                        // position pairs traded (0 = plain pass)
+  uint32_t lpos[QCS_MAX_REMAP];      // the local positions
+  uint32_t my_gbits;                 // bit i = my rank's bit at the global position traded for lpos[i]
+  uint32_t in_tile;                  // bit i: lpos[i] is one of the pass's tile positions
+  uint32_t n_out;                    // pairs whose local position is NOT a tile position ...
+  uint32_t out_pair[QCS_MAX_REMAP];  // ... which pairs, by ascending bit of the tile number ...
+  uint32_t out_tile_bit[QCS_MAX_REMAP];  // ... and which bit of the tile NUMBER each of them is: the low n_out
+                                     // bits of the block index supply these, so tiles bound for different
+                                     // ranks (and tiles that stay) alternate in launch order and the transfer
+                                     // runs underneath the whole pass
+  double2 *peer[1 << QCS_MAX_REMAP];       // [b]: shard of the rank whose traded rank bits are b; [my_gbits] = mine
+  uint32_t *peer_flags[1 << QCS_MAX_REMAP];  // [b]: where that rank expects MY "tile loaded" signals
+  const uint32_t *my_flags;          // my flag words: [s * flag_stride + block] is written by the rank with traded
+                                     // bits s once its CTA `block` holds, in registers, the tile my stores overwrite
+  uint32_t flag_stride;
+  uint32_t epoch;                    // value of this pass (strictly increasing per engine)
+  uint32_t bulk;                     // 1: tiles with data for other ranks leave through shared memory and TMA bulk
+                                     // stores (cp.async.bulk.global.shared::cta, one per contiguous row);
+                                     // 0: 16-byte st.global from the compute threads (same speed, measured)
+  uint32_t row_bits;                 // low tile positions 0..row_bits-1 are contiguous: a row = 16 << row_bits bytes
+  uint32_t *abort_flag;              // my own device word: set when a CTA gave up waiting for a partner (the tile
+                                     // is then NOT stored and the engine reports QCS_CUDA_ERR_CUDA); later CTAs bail out
+  unsigned long long spin_limit;     // clock64 ticks a CTA waits for a partner's signal before giving up
 };
 // fast (ldg8 only): the fused-multiply-add interpreter; `params` must come from a planner run with
 // PlannerConfig::fast_math (fan entries carry product tables instead of single phases).

@@ -31,10 +31,10 @@
 // Signed sums.  Grover's diffusion sums the amplitudes themselves, real and
 // imaginary parts, left to right (src/q_gates.c:334-336).  The same argument
 // holds for signed terms as long as the running sum keeps its sign and binade
-// THROUGHOUT a chunk; that is guaranteed when every term of the chunk has the
-// sign of the running sum (monotone: checking the end points is enough), so a
-// chunk whose terms have mixed signs, or oppose the running sum, is flagged and
-// replayed term by term (`sel` = SEL_RE / SEL_IM below).  Grover's states have
+// THROUGHOUT a chunk; that is guaranteed when all terms of the chunk have one
+// sign (the partial sums are then monotone and lie between the chunk's end
+// points, which are checked), so a chunk whose terms have mixed signs is
+// flagged and replayed term by term (`sel` = SEL_RE / SEL_IM below).  Grover's states have
 // all non-solution amplitudes equal, so the fast path covers them; after a
 // generic circuit most chunks replay (one warp, ~2^n dependent additions).
 // A tree sum is NOT good enough here: the reference's sequential sum of 2^n
@@ -518,21 +518,27 @@ chunk_delta_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mas
     if (d1 != d2) f |= FLAG_TIE;
     if (!same_binade(s1, a1) || !same_binade(s2, a1)) f |= FLAG_CROSS;
     // signed terms: the end points only vouch for the whole chunk when the running sum is monotone,
-    // i.e. every term has the sign of the prefix it is added to
-    if (is_signed && ((any_pos && any_neg) || (any_neg && !(a1 < 0.0)) || (any_pos && !(a1 > 0.0)))) f |= FLAG_CROSS;
+    // i.e. all terms of the chunk have one sign (whichever side of zero the sum is on: a negative sum
+    // climbing through positive terms stays between its end points just the same)
+    if (is_signed && any_pos && any_neg) f |= FLAG_CROSS;
     delta[my_chunk] = d1;
     flag[my_chunk] = f;
   }
 }
 
-// Term-by-term replay of one chunk by a full warp (all lanes keep the same S).
+// Term-by-term replay of one chunk (all lanes return the same S).  The warp fetches 32 terms per
+// round with one coalesced load; lane 0 then adds them in order out of registers handed over by
+// shuffles issued up front, so the dependent chain is the 32 additions alone.
 __device__ __forceinline__ double replay_chunk(const double2 *__restrict__ state, uint64_t first,
                                                uint64_t len, int mask_pos, double S, int lane) {
   for (uint64_t j = 0; j < len; j += 32) {
     const uint64_t i = first + j + lane;
     const double p = (j + lane < len) ? masked_norm(state, i, mask_pos) : 0.0;
+    double t[32];
 #pragma unroll
-    for (int l = 0; l < 32; l++) S = __dadd_rn(S, __shfl_sync(0xffffffffu, p, l));
+    for (int l = 0; l < 32; l++) t[l] = __shfl_sync(0xffffffffu, p, l);
+#pragma unroll
+    for (int l = 0; l < 32; l++) S = __dadd_rn(S, t[l]);
   }
   return S;
 }

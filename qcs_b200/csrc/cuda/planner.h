@@ -42,9 +42,9 @@ struct PassPlan {
   std::vector<int> api_ids; // which ones: indices into plan_passes()'s input, in execution order
                             // (consecutive unless PlannerConfig::reorder)
   int n_fan_headers = 0;    // fan header records among params.n_gates (not gates)
-  int swap_lpos = -1, swap_gpos = -1;  // set by the engine on the executed copy: this pass trades local position
-                            // swap_lpos for global position swap_gpos on its stores (params.n_segments == 0:
-                            // a stand-alone swap, no pass)
+  int n_swaps = 0;          // set by the engine on the executed copy: this pass trades local positions
+  int swap_lpos[3] = {-1, -1, -1}, swap_gpos[3] = {-1, -1, -1};  // swap_lpos[i] for global positions swap_gpos[i]
+                            // on its stores, all at once (params.n_segments == 0: a stand-alone swap, no pass)
   double flops_per_amp;     // planner's cost estimate
   std::vector<int> tile_positions;
 };

@@ -85,6 +85,7 @@ def main():
             c.close(); orc.close()
     # Larger shards (many tiles per rank): swaps ride on the stores of fused passes (SwapStore);
     # the same circuits with stand-alone swap kernels must give the same bits.
+    multi_seen = [0]
     big = {"random_19": (19, po.random_circuit_script(19, 10, seed=5)),
            "qft_20": (20, [("x", 1), ("ry", 19, 0.3), ("h", 18), ("qft",)]),
            "h_top_down_19": (19, [("h", q) for q in reversed(range(19))] + [("cnot", 3, 18), ("cnot", 18, 17)])}
@@ -92,18 +93,25 @@ def main():
         orc = po.Oracle(n, "corrected")
         po.replay(orc, script)
         # swaps on the stores of a pass through TMA bulk stores (default) / 16-byte stores, or stand-alone
+        # and with up to 3 positions traded on one pass (an all-to-all among 2^k ranks) or one at a time
         for fuse, store in (("on", "bulk"), ("on", "thread"), ("off", None)):
             for tile_bits in ((10, 11, 12) if fuse == "on" else (11,)):
-                c = Circuit(n, semantics="corrected", fuse_swaps=fuse, swap_store=store, tile_bits=tile_bits)
-                po.replay(c, script); c.flush(); st = c.stats()
-                first, count = c._shard()
-                got = c.state(); want = orc.state()[first:first + count]
-                tag = f"{name}/fuse_swaps={fuse}/{store}/t{tile_bits}"
-                check(np.all(got == want), f"{tag}: {int(np.sum(got != want))} shard amplitudes differ")
-                check((st["fused_remaps"] > 0) == (fuse == "on"), f"{tag}: fused_remaps={st['fused_remaps']}")
-                if rank == 0:
-                    print(f"done {tag}: passes={st['passes']} remaps={st['remaps']} fused={st['fused_remaps']}", flush=True)
-                c.close()
+                for remap_max in ((3, 1) if fuse == "on" and world >= 4 else (3,)):
+                    c = Circuit(n, semantics="corrected", fuse_swaps=fuse, swap_store=store, tile_bits=tile_bits,
+                                remap_max=remap_max)
+                    po.replay(c, script); c.flush(); st = c.stats()
+                    first, count = c._shard()
+                    got = c.state(); want = orc.state()[first:first + count]
+                    tag = f"{name}/fuse_swaps={fuse}/{store}/t{tile_bits}/remap_max={remap_max}"
+                    check(np.all(got == want), f"{tag}: {int(np.sum(got != want))} shard amplitudes differ")
+                    check((st["fused_remaps"] > 0) == (fuse == "on"), f"{tag}: fused_remaps={st['fused_remaps']}")
+                    if remap_max == 1:
+                        check(st["multi_remaps"] == 0, f"{tag}: multi_remaps={st['multi_remaps']}")
+                    multi_seen[0] += st["multi_remaps"]
+                    if rank == 0:
+                        print(f"done {tag}: passes={st['passes']} remaps={st['remaps']} fused={st['fused_remaps']} "
+                              f"multi={st['multi_remaps']}", flush=True)
+                    c.close()
         # the same circuit in math=fast: whole-queue reordered schedule, swaps riding on its passes
         full = orc.state()
         for fuse in ("on", "off"):
@@ -118,6 +126,8 @@ def main():
                       f"fused={st['fused_remaps']}", flush=True)
             c.close()
         orc.close()
+    if world >= 4:
+        check(multi_seen[0] > 0, "no pass traded more than one position pair on >= 4 ranks")
     # Grover across ranks: the diffusion mean is the reference's sequential sum, continued from rank
     # to rank in basis-index order -- every amplitude equal
     for sem in ("corrected", "reference"):

@@ -72,10 +72,10 @@ def run_plan(passes, n_qubits, fast, state=None):
 
 
 def run_sharded(plans, n_qubits, world, fast, shards=None):
-    """The same for `world` ranks.  plans[rank] = [(PassParams, swap)], swap = None or (lpos, gpos): the
-    pass trades local position lpos for global position gpos on its stores (fused_body.inc OP_STG_SWAP:
-    the element whose bit lpos differs from my rank bit lands in the partner's shard, at the index with
-    bit lpos flipped); an entry with no segments is a stand-alone swap.  Returns the shards."""
+    """The same for `world` ranks.  plans[rank] = [(PassParams, swap)], swap = None or a tuple of up to
+    three (lpos, gpos) pairs: the pass trades local positions lpos for global positions gpos on its
+    stores, all at once (fused_body.inc OP_STG_SWAP); an entry with no segments is a stand-alone swap.
+    Returns the shards."""
     nl = n_qubits - (world.bit_length() - 1)
     if shards is None:
         shards = [np.zeros(1 << nl, dtype=np.complex128) for _ in range(world)]
@@ -101,12 +101,20 @@ def run_sharded(plans, n_qubits, world, fast, shards=None):
             if swap is None:
                 new[rank][addr] = regs
                 continue
-            lpos, gpos = swap
-            gbit = gpos - nl
-            partner, mybit = rank ^ (1 << gbit), (rank >> gbit) & 1
-            away = ((addr >> lpos) & 1) != mybit
-            new[rank][addr[~away]] = regs[~away]
-            new[partner][addr[away] ^ (1 << lpos)] = regs[away]
+            # the kernel's store rule (fused_body.inc OP_STG_SWAP, kernels.h SwapStore): the element's bits
+            # at the traded local positions name the destination rank's traded rank bits; there it sits
+            # at its own index with those bits replaced by MY traded rank bits
+            dest_rank = np.full(addr.shape, rank, dtype=np.int64)
+            dest_addr = addr.astype(np.int64).copy()
+            for lpos, gpos in swap:
+                gbit = gpos - nl
+                b = (addr.astype(np.int64) >> lpos) & 1
+                mine = (rank >> gbit) & 1
+                dest_rank = (dest_rank & ~(1 << gbit)) | (b << gbit)
+                dest_addr = (dest_addr & ~(1 << lpos)) | (mine << lpos)
+            for r2 in range(world):
+                sel = dest_rank == r2
+                new[r2][dest_addr[sel]] = regs[sel]
         assert not any(np.isnan(s).any() for s in new), "every amplitude of every shard is written once"
         shards = new
     return shards

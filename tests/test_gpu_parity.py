@@ -374,6 +374,29 @@ def test_qft30_roundtrip_and_uniform():
     assert st["gates_submitted"] == n * (n + 1) // 2
     assert st["passes"] <= 40, st
     c.close()
+    # QFT of a basis state |x>: every controlled phase now acts on non-zero amplitudes.  Closed form of
+    # the reference's gate order (H(i), then CPHASE(j -> i, pi / 2^(j-i)) for j > i, no final swaps):
+    # qubit i is left in (|0> + e^{i phi_i} |1>) / sqrt 2 with phi_i = pi (x_i + sum_{j>i} x_j / 2^(j-i)),
+    # so <y|QFT|x> = 2^(-n/2) exp(i sum_i y_i phi_i).  4 096 sampled amplitudes, 1e-12 relative
+    # (the CPU reference cannot hold 30 qubits in a test).
+    x = 0x1B2E4D93 & ((1 << n) - 1)
+    c = Circuit(n, semantics="corrected")
+    for q in range(n):
+        if (x >> q) & 1:
+            c.x(q)
+    c.qft()
+    phi = [math.pi * (((x >> i) & 1) + sum(((x >> j) & 1) / float(1 << (j - i)) for j in range(i + 1, n)))
+           for i in range(n)]
+    rng = np.random.default_rng(30)
+    worst = 0.0
+    for y in [0, 1, (1 << n) - 1] + [int(v) for v in rng.integers(0, 1 << n, size=4093)]:
+        out = (ctypes.c_double * 2)()
+        assert C.qcs_cuda_get_amplitude(c.e, y, out) == 0
+        ang = math.fsum(phi[i] for i in range(n) if (y >> i) & 1)
+        want = 2.0 ** (-n / 2) * complex(math.cos(ang), math.sin(ang))
+        worst = max(worst, abs(complex(out[0], out[1]) - want) / abs(want))
+    assert worst <= 1e-12, worst
+    c.close()
     # round trip on a non-trivial basis state
     c = Circuit(n, semantics="corrected")
     x = 0x2F0F3A71 & ((1 << n) - 1)

@@ -318,8 +318,8 @@ def test_kernel_model_reference_semantics():
     assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("mode", ["exact", "fast", "fast-in-order"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("mode", ["exact", "exact-single-swaps", "fast", "fast-in-order"])
 @pytest.mark.parametrize("case", ["brickwork", "qft", "soup"])
 def test_sharded_kernel_model(case, mode, world):
     """Every rank's plan run through the kernel model, position swaps on the stores of the passes that
@@ -330,11 +330,12 @@ def test_sharded_kernel_model(case, mode, world):
     from tests import kernel_emulator as ke
     from tests import plan_emulator as pe
     _, C = _ffi.load()
-    n = 14 if world == 2 else 15
+    n = {2: 14, 4: 15, 8: 16}[world]
     script = {"brickwork": po.random_circuit_script(n, 7, seed=21),
               "qft": [("h", q) for q in range(n)] + [("ry", n - 1, 0.7), ("qft",)],
               "soup": _mixed_script(n, 160, 17)}[case]
-    kw = {"exact": {}, "fast": {"math": "fast"}, "fast-in-order": {"math": "fast", "reorder": "off"}}[mode]
+    kw = {"exact": {}, "exact-single-swaps": {"remap_max": 1}, "fast": {"math": "fast"},
+          "fast-in-order": {"math": "fast", "reorder": "off"}}[mode]
     plans, layouts = [], []
     try:
         for rank in range(world):
@@ -345,9 +346,9 @@ def test_sharded_kernel_model(case, mode, world):
             c.flush()
             entries = []
             for k, p in enumerate(pe.read_plan(c)):
-                lpos, gpos = ctypes.c_int(-1), ctypes.c_int(-1)
-                has = C.qcs_cuda_last_plan_swap(c.e, k, ctypes.byref(lpos), ctypes.byref(gpos))
-                entries.append((p, (lpos.value, gpos.value) if has else None))
+                lpos, gpos = (ctypes.c_int * 3)(-1, -1, -1), (ctypes.c_int * 3)(-1, -1, -1)
+                cnt = C.qcs_cuda_last_plan_swap(c.e, k, lpos, gpos)
+                entries.append((p, tuple((lpos[i], gpos[i]) for i in range(cnt)) if cnt else None))
             plans.append(entries)
             layouts.append(c.layout())
             c.close()
@@ -355,7 +356,13 @@ def test_sharded_kernel_model(case, mode, world):
         C.qcs_cuda_dist_finalize()
     assert all(l == layouts[0] for l in layouts), "ranks disagree on the layout"
     assert any(sw is not None for _, sw in plans[0]), "the case must exercise a position swap"
-    shards = ke.run_sharded(plans, n, world, fast=(mode != "exact"))
+    most = max(len(sw) for _, sw in plans[0] if sw is not None)
+    if mode == "exact-single-swaps" or mode == "fast":
+        assert most == 1
+    elif mode == "exact" and world >= 4 and case != "soup":
+        # in-order schedules trade several positions on one pass (an all-to-all among 2^k ranks)
+        assert most >= (3 if world == 8 and case == "brickwork" else 2), most
+    shards = ke.run_sharded(plans, n, world, fast=not mode.startswith("exact"))
     phys = np.concatenate(shards)
     logical = np.arange(1 << n, dtype=np.int64)
     where = np.zeros_like(logical)
