@@ -499,13 +499,21 @@ def main() -> None:
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    phase_s = {"qc_create": 0.0, "gates + qc_find_most_likely_state": 0.0, "qc_get_probability": 0.0, "qc_destroy": 0.0}
     for _ in range(e2e_steps):
+        ta = time.perf_counter()
         ce = Circuit(n, **kw)                      # qc_create: buffers from the pool; |0...0> is not written out
+        tb = time.perf_counter()
         ce.qft()                                   # 465 qc_h / qc_cphase calls (queued)
         best = ce.find_most_likely_state()         # flush: the fused passes, argmax candidates from the last one, D2H
+        tc = time.perf_counter()
         prob = ce.get_probability(12345)           # D2H of one amplitude
+        td = time.perf_counter()
         d2h += 16 + 16
         ce.close()                                 # qc_destroy
+        te = time.perf_counter()
+        for key, dt in zip(phase_s, (tb - ta, tc - tb, td - tc, te - td)):
+            phase_s[key] += dt
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -613,6 +621,7 @@ def main() -> None:
         },
         "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": h2d_per_step,
                 "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps,
+                "host_ms_per_step_by_call": {k2: 1e3 * v / e2e_steps for k2, v in phase_s.items()},
                 "what": "qc_create + qc_quantum_fourier_transform + qc_find_most_likely_state + "
                         "qc_get_probability + qc_destroy through libqcs.so"},
         "gpu_launches": st["kernel_launches"],

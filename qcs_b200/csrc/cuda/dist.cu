@@ -134,6 +134,42 @@ p2p_swap_kernel(double2 *__restrict__ mine, double2 *__restrict__ peer, uint64_t
 
 }  // namespace
 
+// ---- peer mappings and flag arrays outlive the engines that first needed them ----------------------
+// Programs in the reference's style create and destroy circuits freely; on a sharded engine every
+// qc_create used to open 2 x (world - 1) CUDA IPC handles (milliseconds each for a 16 GiB buffer),
+// allocate and clear a flag array and close everything again in qc_destroy -- a quarter of the
+// end-to-end time of a 33-qubit QFT on 8 GPUs (BENCH_r01 / SCALE_r01).  State buffers come back from
+// the buffer pool with the same address and the same IPC handle, so the mappings are cached by
+// (rank, handle) until qcs_cuda_dist_finalize; a buffer a peer may still have mapped is pinned in the
+// pool (pool_pin, engine.cu) so that it is never freed underneath that mapping.
+namespace {
+struct PeerMapping {
+  int rank;
+  cudaIpcMemHandle_t handle;
+  void *ptr;
+};
+std::vector<PeerMapping> g_peer_maps;
+struct FlagArray {
+  size_t n_tiles;
+  uint32_t *ptr;
+  bool in_use;  // engines alive at the same time never share one (their passes could interleave)
+};
+std::vector<FlagArray> g_flag_arrays;
+uint32_t g_swap_epoch = 0;  // one sequence for all engines of the process: flag arrays are reused, epochs are not
+
+void *open_peer_cached(int rank, const cudaIpcMemHandle_t &h) {
+  for (const PeerMapping &m : g_peer_maps)
+    if (m.rank == rank && std::memcmp(&m.handle, &h, sizeof(h)) == 0) return m.ptr;
+  void *ptr = nullptr;
+  if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  g_peer_maps.push_back(PeerMapping{rank, h, ptr});
+  return ptr;
+}
+}  // namespace
+
 // Exchanges CUDA IPC handles of every rank's state buffer and tile-flag array so that partners
 // can address them.
 int dist_open_peers(Engine &e) {
@@ -144,16 +180,27 @@ int dist_open_peers(Engine &e) {
     // per sending rank of a remap group (<= 2^QCS_MAX_REMAP) one word per tile + (behind them) the
     // abort word of the bounded handshake wait
     const size_t words = (n_tiles << QCS_MAX_REMAP) + 1;
-    CK(cudaMalloc(&e.tile_flags, words * sizeof(uint32_t)));
-    CK(cudaMemset(e.tile_flags, 0, words * sizeof(uint32_t)));
+    for (FlagArray &f : g_flag_arrays)
+      if (f.n_tiles == n_tiles && !f.in_use) {
+        f.in_use = true;
+        e.tile_flags = f.ptr;
+        break;
+      }
+    if (!e.tile_flags) {
+      CK(cudaMalloc(&e.tile_flags, words * sizeof(uint32_t)));
+      CK(cudaMemset(e.tile_flags, 0, words * sizeof(uint32_t)));
+      g_flag_arrays.push_back(FlagArray{n_tiles, e.tile_flags, true});
+    }
     e.tile_flag_stride = (uint32_t)n_tiles;
     e.swap_abort_flag = e.tile_flags + (n_tiles << QCS_MAX_REMAP);
+    CK(cudaMemsetAsync(e.swap_abort_flag, 0, sizeof(uint32_t), e.stream));
     if (!e.swap_status_host) CK(cudaMallocHost(&e.swap_status_host, sizeof(int)));
     *e.swap_status_host = 0;
   }
   struct Handles { cudaIpcMemHandle_t live, flags; } mine;
   std::memset(&mine, 0, sizeof(mine));
   CK(cudaIpcGetMemHandle(&mine.live, e.live));
+  pool_pin(e.live);  // peers keep it mapped after this engine is gone
   if (e.tile_flags) CK(cudaIpcGetMemHandle(&mine.flags, e.tile_flags));
   std::vector<Handles> all(d.world);
   int rc = dist_allgather_host(&mine, all.data(), sizeof(mine));
@@ -166,12 +213,9 @@ int dist_open_peers(Engine &e) {
       e.peer_flags[r] = e.tile_flags;
       continue;
     }
-    void *ptr = nullptr, *fptr = nullptr;
-    cudaError_t ce = cudaIpcOpenMemHandle(&ptr, all[r].live, cudaIpcMemLazyEnablePeerAccess);
-    if (ce == cudaSuccess && e.tile_flags)
-      ce = cudaIpcOpenMemHandle(&fptr, all[r].flags, cudaIpcMemLazyEnablePeerAccess);
-    if (ce != cudaSuccess) {
-      cudaGetLastError();
+    void *ptr = open_peer_cached(r, all[r].live);
+    void *fptr = (ptr && e.tile_flags) ? open_peer_cached(r, all[r].flags) : nullptr;
+    if (!ptr || (e.tile_flags && !fptr)) {
       e.peer_live.clear();  // no peer access: the NCCL path stays in charge
       e.peer_flags.clear();
       return QCS_CUDA_OK;
@@ -182,19 +226,28 @@ int dist_open_peers(Engine &e) {
   return QCS_CUDA_OK;
 }
 
+// qc_destroy: the mappings stay (cache above); the flag array goes back on the shelf.
 void dist_close_peers(Engine &e) {
-  DistContext &d = dist();
-  for (int r = 0; r < (int)e.peer_live.size(); r++)
-    if (r != d.rank && e.peer_live[r]) cudaIpcCloseMemHandle(e.peer_live[r]);
-  for (int r = 0; r < (int)e.peer_flags.size(); r++)
-    if (r != d.rank && e.peer_flags[r]) cudaIpcCloseMemHandle(e.peer_flags[r]);
   e.peer_live.clear();
   e.peer_flags.clear();
-  if (e.tile_flags) cudaFree(e.tile_flags);
+  for (FlagArray &f : g_flag_arrays)
+    if (f.ptr == e.tile_flags) f.in_use = false;
   e.tile_flags = nullptr;
   e.swap_abort_flag = nullptr;
   if (e.swap_status_host) cudaFreeHost(e.swap_status_host);
   e.swap_status_host = nullptr;
+}
+
+// qcs_cuda_dist_finalize: every rank closes what it mapped, then (behind a barrier) frees what it exported.
+static void release_peer_cache() {
+  for (const PeerMapping &m : g_peer_maps) cudaIpcCloseMemHandle(m.ptr);
+  g_peer_maps.clear();
+  double dummy = 0.0;
+  std::vector<double> all(dist().world > 0 ? dist().world : 1);
+  dist_allgather_host(&dummy, all.data(), sizeof(double));  // nobody maps my buffers any more
+  for (const FlagArray &f : g_flag_arrays) cudaFree(f.ptr);
+  g_flag_arrays.clear();
+  pool_unpin_all();
 }
 
 static int stream_barrier(Engine &e, cudaStream_t stream) {
@@ -249,7 +302,8 @@ bool dist_fused_swap_args(Engine &e, int k, const int *lpos, const int *gpos, Sw
   }
   sw.my_flags = e.tile_flags;
   sw.flag_stride = e.tile_flag_stride;
-  sw.epoch = ++e.swap_epoch;
+  sw.epoch = ++g_swap_epoch;
+  e.swap_epoch = sw.epoch;
   sw.abort_flag = e.swap_abort_flag;
   sw.spin_limit = swap_spin_limit();
   return true;  // in_tile, n_out, out_pair, out_tile_bit, bulk, row_bits: the caller knows the pass's tile
@@ -464,6 +518,7 @@ int qcs_cuda_dist_init_plan_only(int rank, int world) {
 
 int qcs_cuda_dist_finalize(void) {
   DistContext &d = dist();
+  if (d.comm) release_peer_cache();
   if (d.comm) ncclCommDestroy((ncclComm_t)d.comm);
   if (g_small_dev) cudaFree(g_small_dev);
   g_small_dev = nullptr;

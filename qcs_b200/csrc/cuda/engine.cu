@@ -146,6 +146,8 @@ static int load_options(Options &o) {
 namespace {
 struct PoolEntry { void *ptr; size_t bytes; int device; };
 std::vector<PoolEntry> g_pool;
+std::vector<void *> g_pinned;  // see pool_pin (engine.h)
+bool is_pinned(void *p) { return std::find(g_pinned.begin(), g_pinned.end(), p) != g_pinned.end(); }
 constexpr size_t kPoolSlots = 6;
 constexpr size_t kPoolBytes = (size_t)40 << 30;  // never sit on more than 40 GiB of freed buffers
 bool pool_enabled() {
@@ -157,8 +159,12 @@ bool pool_enabled() {
   return on == 1;
 }
 void pool_trim_locked() {
-  for (auto &p : g_pool) cudaFree(p.ptr);
-  g_pool.clear();
+  std::vector<PoolEntry> keep;
+  for (auto &p : g_pool) {
+    if (is_pinned(p.ptr)) keep.push_back(p);
+    else cudaFree(p.ptr);
+  }
+  g_pool.swap(keep);
 }
 cudaError_t pool_alloc(void **out, size_t bytes) {
   std::lock_guard<std::mutex> lock(globals_mutex());
@@ -181,27 +187,44 @@ cudaError_t pool_alloc(void **out, size_t bytes) {
 }
 void pool_free(void *ptr, size_t bytes) {
   if (!ptr) return;
-  if (!pool_enabled() || bytes < (1u << 20)) {
+  std::lock_guard<std::mutex> lock(globals_mutex());
+  const bool pinned = is_pinned(ptr);
+  if (!pinned && (!pool_enabled() || bytes < (1u << 20) || bytes > kPoolBytes)) {
     cudaFree(ptr);
     return;
   }
   int dev = 0;
   cudaGetDevice(&dev);
-  if (bytes > kPoolBytes) {
-    cudaFree(ptr);
-    return;
-  }
-  std::lock_guard<std::mutex> lock(globals_mutex());
   g_pool.push_back(PoolEntry{ptr, bytes, dev});
-  size_t total = 0;
-  for (auto &p : g_pool) total += p.bytes;
-  while (g_pool.size() > kPoolSlots || total > kPoolBytes) {  // evict oldest first
-    total -= g_pool.front().bytes;
-    cudaFree(g_pool.front().ptr);
-    g_pool.erase(g_pool.begin());
+  size_t total = 0, unpinned = 0;
+  for (auto &p : g_pool) {
+    if (is_pinned(p.ptr)) continue;
+    total += p.bytes;
+    unpinned++;
+  }
+  for (size_t i = 0; i < g_pool.size() && (unpinned > kPoolSlots || total > kPoolBytes);) {  // evict oldest first
+    if (is_pinned(g_pool[i].ptr)) {
+      i++;
+      continue;
+    }
+    total -= g_pool[i].bytes;
+    unpinned--;
+    cudaFree(g_pool[i].ptr);
+    g_pool.erase(g_pool.begin() + (long)i);
   }
 }
 }  // namespace
+
+void pool_pin(void *ptr) {
+  std::lock_guard<std::mutex> lock(globals_mutex());
+  if (ptr && !is_pinned(ptr)) g_pinned.push_back(ptr);
+}
+
+void pool_unpin_all() {
+  std::lock_guard<std::mutex> lock(globals_mutex());
+  g_pinned.clear();
+  pool_trim_locked();
+}
 
 // ------------------------------------------------------------------ events / stats
 static cudaEvent_t get_event(Engine &e) {
@@ -1094,10 +1117,9 @@ void qcs_cuda_state_destroy(qcs_cuda_engine *e) {
     return;
   }
   if (e->stream) cudaStreamSynchronize(e->stream);
-  if (!e->peer_live.empty()) {
-    dist_barrier(*e);  // nobody still addresses this buffer
-    dist_close_peers(*e);
-  }
+  // (no barrier: every pass or swap through which a peer wrote into this buffer was followed by an
+  // all-reduce on the streams of both ranks, and this rank's stream has just been drained)
+  if (dist().active) dist_close_peers(*e);
   for (auto &pp : e->pending_pass_events) { cudaEventDestroy(pp.begin); cudaEventDestroy(pp.end); }
   for (auto &pr : e->pending_xchg_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);

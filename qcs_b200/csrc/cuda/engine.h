@@ -126,6 +126,10 @@ struct Engine {
 };
 
 // engine.cu
+// a pooled buffer whose CUDA IPC handle other ranks may hold mapped: never cudaFree'd (it stays in the
+// pool, whatever the pool's size limits say) until pool_unpin_all
+void pool_pin(void *ptr);
+void pool_unpin_all();
 int set_error(int code, const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
 

@@ -443,11 +443,19 @@ chunk_scan_kernel(const double *chunk_sum, uint64_t n_chunks, const double *star
   for (uint64_t c = lo; c < hi; c++) s += chunk_sum[c];
   sh[threadIdx.x] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double run = start;
-    for (int t = 0; t < 1024; t++) {
-      const double v = sh[t];
-      sh[t] = run;
+  if (threadIdx.x < 32) {  // exclusive scan of the 1024 partials by one warp: 32 per lane + a shuffle scan
+    double mine = 0.0;
+    for (int t = 0; t < 32; t++) mine += sh[threadIdx.x * 32 + t];
+    double incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double v = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)threadIdx.x >= o) incl += v;
+    }
+    double run = start + (incl - mine);
+    for (int t = 0; t < 32; t++) {
+      const double v = sh[threadIdx.x * 32 + t];
+      sh[threadIdx.x * 32 + t] = run;
       run += v;
     }
   }
@@ -564,17 +572,23 @@ group_sum_kernel(const double *__restrict__ delta, const double *__restrict__ ap
   const uint64_t first = g * RESOLVE_GROUP;
   const uint64_t last = first + RESOLVE_GROUP < n_chunks ? first + RESOLVE_GROUP : n_chunks;
   double s = 0.0;
-  int f = 0;
+  int f = 0, signs = 0;
   for (uint64_t c = first + lane; c < last; c += 32) {
     const int fc = flag[c];
     f |= fc;
-    if (!(fc & FLAG_ZERO)) s += delta[c];  // exact: multiples of one quantum, total below the binade's top
+    if (!(fc & FLAG_ZERO)) {
+      const double d = delta[c];
+      s += d;  // exact: multiples of one quantum, total below the binade's top
+      signs |= (d > 0.0 ? 1 : 0) | (d < 0.0 ? 2 : 0);
+    }
   }
   s = warp_sum(s);
   f = __reduce_or_sync(0xffffffffu, f);
+  signs = __reduce_or_sync(0xffffffffu, signs);
   if (lane == 0) {
     unsigned char out = 0;
     if (f & (FLAG_TIE | FLAG_CROSS)) out = 1;
+    if (signs == 3) out = 1;  // signed sums: the running sum is not monotone across the group
     if (!same_binade(approx[first], approx[last - 1])) out = 1;
     gsum[g] = s;
     gflag[g] = out;
@@ -600,6 +614,37 @@ __device__ __forceinline__ double walk_chunks(const double2 *__restrict__ state,
     }
     double my_exact = 0.0;
     const int lim = (int)((c_end - base) < 32 ? (c_end - base) : 32);
+    if (have_deltas) {
+      // Shortcut over the whole block of 32 chunks: when none of them is flagged, their approximate
+      // prefixes share the running sum's binade and their increments share one sign, the walk below
+      // would perform 32 EXACT additions of multiples of the binade's quantum (monotone, so the end
+      // point vouches for every step) -- the same numbers come out of one warp scan.
+      const bool live = mine < c_end && !(my_f & FLAG_ZERO);
+      const unsigned nz = __ballot_sync(0xffffffffu, live);
+      if (nz == 0u) {
+        if (mine < c_end) exact[mine] = S;
+        continue;
+      }
+      const double a_ref = __shfl_sync(0xffffffffu, my_a, __ffs((int)nz) - 1);
+      const unsigned bad = __ballot_sync(0xffffffffu, live && ((my_f & (FLAG_TIE | FLAG_CROSS)) || !same_binade(my_a, a_ref)));
+      const unsigned pos = __ballot_sync(0xffffffffu, live && my_d > 0.0);
+      const unsigned neg = __ballot_sync(0xffffffffu, live && my_d < 0.0);
+      if (bad == 0u && !(pos && neg) && same_binade(S, a_ref)) {
+        const double dz = live ? my_d : 0.0;
+        double incl = dz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const double Snew = __dadd_rn(S, __shfl_sync(0xffffffffu, incl, 31));
+        if (same_binade(Snew, S)) {
+          if (mine < c_end) exact[mine] = S + (incl - dz);
+          S = Snew;
+          continue;
+        }
+      }
+    }
     for (int j = 0; j < lim; j++) {
       const double d = __shfl_sync(0xffffffffu, my_d, j);
       const double a = __shfl_sync(0xffffffffu, my_a, j);
