@@ -764,8 +764,10 @@ def random_circuit_aux(Circuit, kw, world, barrier, dist, torch) -> dict:
             "amplitude_gate_updates_per_s_per_gpu": len(script) * 2.0 ** n / dev_s / world,
             "remaps": st["remaps"], "fused_remaps": st["fused_remaps"],
             "fused_remap_pass_ms_avg": (st["fused_remap_pass_ms"] / st["fused_remaps"]) if st["fused_remaps"] else None,
-            "nvlink_GBps_per_direction_in_fused_passes": (st["fused_remaps"] * 8.0 * 2.0 ** (n - int(math.log2(world)))
-                                                          / (st["fused_remap_pass_ms"] * 1e-3) / 1e9
+            "position_pairs_traded": st["remaps"], "carrying_passes_with_2_or_3_pairs": st["multi_remaps"],
+            "nvlink_GBps_per_direction_in_fused_passes": (st["fused_remap_bytes"] / (st["fused_remap_pass_ms"] * 1e-3) / 1e9
+                                                          if st["fused_remap_pass_ms"] else None),
+            "nvlink_frac_of_measured_peer_copy_770GBps": (st["fused_remap_bytes"] / (st["fused_remap_pass_ms"] * 1e-3) / 1e9 / 770.0
                                                           if st["fused_remap_pass_ms"] else None),
             "plain_pass_ms_avg": ((st["pass_ms"] - st["fused_remap_pass_ms"]) / max(1, st["passes"] - st["fused_remaps"])),
             "exchange_ms": st["exchange_ms"], "pass_ms": st["pass_ms"],

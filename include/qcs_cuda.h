@@ -144,6 +144,7 @@ typedef struct qcs_cuda_stats {
                                   amplitude, summed over executed passes     */
   long gates_cancelled;        /* dropped by the queue peephole (exact pairs) */
   long multi_remaps;           /* carrying passes that traded 2 or 3 position pairs at once (counted in fused_remaps) */
+  double fused_remap_bytes;    /* bytes per direction this rank moved over NVLink inside carrying passes (part of exchange_bytes) */
 } qcs_cuda_stats;
 
 int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out);

@@ -31,7 +31,7 @@ class Stats(ctypes.Structure):
         ("exchange_bytes", _D), ("exchange_ms", _D),
         ("fused_remaps", ctypes.c_long), ("fused_remap_pass_ms", _D),
         ("pass_flops_per_amp", _D), ("gates_cancelled", ctypes.c_long),
-        ("multi_remaps", ctypes.c_long),
+        ("multi_remaps", ctypes.c_long), ("fused_remap_bytes", _D),
     ]
 
     def as_dict(self) -> dict:

@@ -623,6 +623,7 @@ static int run_range_reordered(Engine &e, const std::vector<HostGate> &q, size_t
     if (ride) {
       RC(launch_passes(e, plan, 0, n_run, &sw, 1, &victim, &gpos));
       note_swap(e, victim, gpos);
+      e.fused_swap_bytes += 8.0 * (double)e.local_size;
       e.fused_swaps++;
     } else {
       RC(launch_passes(e, plan, 0, n_run, nullptr));  // nothing to ride on, or no peer mapping
@@ -716,6 +717,7 @@ static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, si
     for (int j = 0; j < k_pairs; j++) note_swap(e, lpos_k[j], gpos_k[j]);
     // bytes that crossed NVLink per direction: (1 - 2^-k) of the shard, not k halves
     e.exchange_bytes += (16.0 * (1.0 - std::ldexp(1.0, -k_pairs)) - 8.0 * k_pairs) * (double)e.local_size;
+    e.fused_swap_bytes += 16.0 * (1.0 - std::ldexp(1.0, -k_pairs)) * (double)e.local_size;
     e.fused_swaps++;
     if (k_pairs > 1) e.multi_remaps++;
     i = pass_end;  // the rest of the batch is planned again under the new layout
@@ -1502,6 +1504,7 @@ int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out) {
   out->pass_flops_per_amp = e->pass_flops_per_amp;
   out->gates_cancelled = e->gates_cancelled;
   out->multi_remaps = e->multi_remaps;
+  out->fused_remap_bytes = e->fused_swap_bytes;
   return QCS_CUDA_OK;
 }
 
@@ -1511,6 +1514,7 @@ int qcs_cuda_reset_stats(qcs_cuda_engine *e) {
   e->gates_submitted = e->gates_executed = e->passes = e->kernel_launches = e->segments = e->remaps = 0;
   e->algorithmic_bytes = e->pass_bytes = e->pass_ms = e->exchange_bytes = e->exchange_ms = 0;
   e->fused_swaps = 0;
+  e->fused_swap_bytes = 0;
   e->multi_remaps = 0;
   e->gates_cancelled = 0;
   e->fused_swap_pass_ms = 0;

@@ -112,6 +112,7 @@ struct Engine {
   long long fused_swaps = 0;   // remaps that rode on a pass instead of getting a kernel of their own
   double algorithmic_bytes = 0, pass_bytes = 0, pass_ms = 0, exchange_bytes = 0, exchange_ms = 0;
   double pass_flops_per_amp = 0;  // planner's FP64 operation count per amplitude, summed over executed passes
+  double fused_swap_bytes = 0;    // bytes per direction moved inside carrying passes
   double fused_swap_pass_ms = 0;  // device time of the passes that carried a swap (also in pass_ms)
   bool timing = false;
   // one event pair per launched pass (timing on): folded into pass_ms / fused_swap_pass_ms and, for the

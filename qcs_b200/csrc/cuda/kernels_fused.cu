@@ -374,7 +374,7 @@ static int tile_row_bits(const PassParams &p) {
 
 }  // namespace
 
-using LdgKernel = void (*)(double2 *, const PassParams, uint32_t, const SwapStore, const PassExtras);
+using LdgKernel = void (*)(double2 *, const PassParams, uint32_t, const SwapStore, const PassExtras, uint32_t);
 
 // [math=fast][16 amplitudes per thread][tile bits - 10]
 static LdgKernel ldg_kernel(bool fast, bool r4, int T) {
@@ -448,7 +448,13 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
       if (e != cudaSuccess) return e;
       configured = true;
     }
-    k<<<n_tiles, 1u << (T - params.reg_bits), smem, stream>>>(state, params, pass_flags, sw, ex);
+    // a pass that carries a remap runs persistent: every CTA resident at once (fused_body.inc)
+    unsigned grid = n_tiles;
+    if (swap && sw.k) {
+      const unsigned resident = (unsigned)sm_count * (r4 ? (T == 12 ? 2u : T == 11 ? 3u : 8u) : (8u >> (T - QCS_MIN_TILE_BITS)));
+      if (grid > resident) grid = resident;
+    }
+    k<<<grid, 1u << (T - params.reg_bits), smem, stream>>>(state, params, pass_flags, sw, ex, n_tiles);
     return cudaGetLastError();
   }
   const size_t smem_tma = (size_t)kSlots * kTileBytes + 128;  // slots + barriers + tile origins

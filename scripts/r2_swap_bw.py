@@ -38,7 +38,7 @@ def run(script, label, reps=2, **kw):
     if rank == 0:
         fr = st["fused_remaps"]
         fms = st["fused_remap_pass_ms"] / fr if fr else 0.0
-        gbs = 8.0 * 2.0 ** nl / (fms * 1e-3) / 1e9 if fms else 0.0
+        gbs = st["fused_remap_bytes"] / fr / (fms * 1e-3) / 1e9 if fms else 0.0
         print(f"{label:34s} n={n} {float(t[0]):8.2f} ms passes={st['passes'] // reps} remaps={st['remaps'] // reps} fused={fr // reps} "
               f"carrying pass {fms:6.2f} ms = {gbs:4.0f} GB/s/dir; plain {(st['pass_ms'] - st['fused_remap_pass_ms']) / max(1, st['passes'] - fr):6.2f} ms "
               f"[{' '.join(f'{x:.1f}' for x in c.pass_times())}]", flush=True)
