@@ -97,6 +97,10 @@ static int load_options(Options &o) {
   else return set_error(QCS_CUDA_ERR_INVALID, "exchange must be p2p|nccl, got '%s'", v.c_str());
   v = option_value("fuse_swaps");
   o.fuse_swaps = !(v == "off" || v == "0");
+  v = option_value("victim_policy");
+  if (v == "lru") o.victim_policy = 0;
+  else if (v.empty() || v == "mru") o.victim_policy = 1;
+  else return set_error(QCS_CUDA_ERR_INVALID, "victim_policy must be mru|lru, got '%s'", v.c_str());
   v = option_value("remap_max");
   if (!v.empty()) o.remap_max = std::atoi(v.c_str());
   if (o.remap_max < 1 || o.remap_max > QCS_MAX_REMAP) o.remap_max = Options().remap_max;
@@ -502,11 +506,21 @@ static VictimRanking rank_victims(const Engine &e, const std::vector<HostGate> &
     else if (last_use[pos] < 0) last_use[pos] = (long)i;
   }
   for (int pos = e.nl - 1; pos >= lowest && pos >= 0; pos--) vr.order.push_back(pos);
-  // farthest next use first; then the longest idle; then positions every tile contains (only offered
-  // when lowest < 5: whatever arrives there is pairable in every later pass); then the highest
+  // Farthest next use first (Belady).  Ties only arise between positions the queue never pairs again;
+  // among those: one it has not paired at all in this window, then -- the queue says nothing about
+  // the future, but circuits sweep their qubits layer after layer -- the MOST recently paired one
+  // (a cyclic sweep comes back to it last; evicting the least recently paired one instead costs a
+  // repeated QFT a second remap per round, stand-alone at that: nothing runs before the first gate of
+  // the next round for it to ride on); then positions every tile contains (only offered when
+  // lowest < 5: whatever arrives there is pairable in every later pass); then the highest.
+  const bool mru = e.opt.victim_policy == 1;
   std::stable_sort(vr.order.begin(), vr.order.end(), [&](int a, int b) {
     if (vr.next_use[a] != vr.next_use[b]) return vr.next_use[a] > vr.next_use[b];
-    if (last_use[a] != last_use[b]) return last_use[a] < last_use[b];
+    if (last_use[a] != last_use[b]) {
+      if (!mru) return last_use[a] < last_use[b];
+      if ((last_use[a] < 0) != (last_use[b] < 0)) return last_use[a] < 0;
+      return last_use[a] > last_use[b];
+    }
     return (a < QCS_LANE_BITS) && !(b < QCS_LANE_BITS);
   });
   if (vr.order.empty()) vr.order.push_back(e.nl - 1);

@@ -35,6 +35,8 @@ struct Options {
   int reorder_segments = 8;
   bool peephole = true;    // drop exactly self-cancelling gate pairs from the queue (corrected semantics)
   bool fuse_swaps = true;  // fold position swaps into the stores of a pass (peer-memory path only)
+  int victim_policy = 1;   // which local position leaves when the queue pairs none of the candidates again:
+                           // 1 the most recently paired (cyclic sweeps), 0 the least recently paired
   int remap_max = 3;       // position pairs one carrying pass may trade (1..3): an all-to-all among 2^k ranks
   bool fuse_argmax = true; // qc_find_most_likely_state folds its first reduction level into the pass it flushes
   bool lazy_init = true;   // qc_create writes nothing; see Engine::zero_ket_pending

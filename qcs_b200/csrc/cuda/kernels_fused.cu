@@ -448,9 +448,14 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
       if (e != cudaSuccess) return e;
       configured = true;
     }
-    // a pass that carries a remap runs persistent: every CTA resident at once (fused_body.inc)
+    // One CTA per tile.  (A remap-carrying pass was also tried PERSISTENT -- as many CTAs as are resident,
+    // each looping over its tiles with the bulk stores of tile i draining while it loads and computes
+    // tile i + 1, QCS_CUDA_PERSISTENT_REMAP=1 -- and was 15-40 % slower: CTAs that all start together
+    // and loop stay in lock step, so loads, FP64 work and stores no longer overlap ACROSS CTAs, which
+    // is worth more than the overlap gained inside one; profiles/r2g_swap_bw_persistent.log.)
     unsigned grid = n_tiles;
-    if (swap && sw.k) {
+    static const bool persistent_remap = getenv("QCS_CUDA_PERSISTENT_REMAP") && atoi(getenv("QCS_CUDA_PERSISTENT_REMAP")) != 0;
+    if (swap && sw.k && persistent_remap) {
       const unsigned resident = (unsigned)sm_count * (r4 ? (T == 12 ? 2u : T == 11 ? 3u : 8u) : (8u >> (T - QCS_MIN_TILE_BITS)));
       if (grid > resident) grid = resident;
     }
