@@ -181,3 +181,27 @@ def test_bench_reference_arm_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "gates/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_circuit_options_do_not_clobber_process_defaults(libs):
+    """Circuit(..., semantics=...) passes options as process-wide defaults around qc_create; a default the
+    caller had set before must still be there afterwards (round-1 advice: it used to be wiped)."""
+    from qcs_b200 import Circuit
+    from qcs_b200.circuit import get_default, set_default
+    try:
+        set_default("semantics", "corrected")
+        set_default("tile_bits", "12")
+        c = Circuit(3, dryrun=True, semantics="reference", tile_bits=10)
+        c.close()
+        assert get_default("semantics") == "corrected" and get_default("tile_bits") == "12"
+        assert get_default("dryrun") is None              # was not set before: not left behind either
+        c = Circuit(3, dryrun=True)                       # no explicit option: the caller's default applies
+        c.h(0); c.cnot(0, 1); c.flush()
+        kinds = [t[1] for t in c.trace() if t[0] == "gate"]
+        assert len(kinds) == 2
+        c.close()
+    finally:
+        set_default("semantics", None)
+        set_default("tile_bits", None)
+    from qcs_b200 import _ffi
+    assert _ffi.load()[1].qcs_cuda_trim_pool() >= 0
