@@ -500,15 +500,16 @@ chunk_delta_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mas
   bool any_pos = false, any_neg = false;
   const int n_rows = (int)((n_chunks - c0) < 32 ? (n_chunks - c0) : 32);
   for (int j = 0; j < SEQ_CHUNK / 32; j++) {
-#pragma unroll 8
-    for (int c = 0; c < 32; c++) {
-      double p = 0.0;
-      if (c < n_rows)
-        p = masked_norm(state, (c0 + c) * SEQ_CHUNK + (uint64_t)j * 32 + lane, mask_pos);
-      stage[wib][c][lane] = p;
-    }
+    // all 32 row loads of this step are issued before the first is used: on small shards (a 24-qubit
+    // Grover search has 512 warps in this kernel) nothing else hides their latency
+    double pv[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++)
+      pv[c] = c < n_rows ? masked_norm(state, (c0 + c) * SEQ_CHUNK + (uint64_t)j * 32 + lane, mask_pos) : 0.0;
+#pragma unroll
+    for (int c = 0; c < 32; c++) stage[wib][c][lane] = pv[c];
     __syncwarp();
-#pragma unroll 8
+#pragma unroll
     for (int k = 0; k < 32; k++) {
       const double p = stage[wib][lane][k];
       s1 = __dadd_rn(s1, p);
@@ -534,19 +535,23 @@ chunk_delta_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mas
   }
 }
 
-// Term-by-term replay of one chunk (all lanes return the same S).  The warp fetches 32 terms per
-// round with one coalesced load; lane 0 then adds them in order out of registers handed over by
-// shuffles issued up front, so the dependent chain is the 32 additions alone.
+// Term-by-term replay of one chunk of at most SEQ_CHUNK terms (all lanes return the same S).  The
+// warp fetches the whole chunk with 32 independent coalesced loads (one memory latency instead of 32
+// in a row: the walk that calls this is a single warp); the terms then reach the additions through
+// shuffles that do not depend on S, so the dependent chain is the 1 024 additions alone.  Positions
+// past `len` contribute +0.0 (S + 0.0 == S).
 __device__ __forceinline__ double replay_chunk(const double2 *__restrict__ state, uint64_t first,
                                                uint64_t len, int mask_pos, double S, int lane) {
-  for (uint64_t j = 0; j < len; j += 32) {
-    const uint64_t i = first + j + lane;
-    const double p = (j + lane < len) ? masked_norm(state, i, mask_pos) : 0.0;
-    double t[32];
+  double p[SEQ_CHUNK / 32];
 #pragma unroll
-    for (int l = 0; l < 32; l++) t[l] = __shfl_sync(0xffffffffu, p, l);
+  for (int j = 0; j < SEQ_CHUNK / 32; j++) {
+    const uint64_t off = (uint64_t)j * 32 + lane;
+    p[j] = off < len ? masked_norm(state, first + off, mask_pos) : 0.0;
+  }
 #pragma unroll
-    for (int l = 0; l < 32; l++) S = __dadd_rn(S, t[l]);
+  for (int j = 0; j < SEQ_CHUNK / 32; j++) {
+#pragma unroll
+    for (int l = 0; l < 32; l++) S = __dadd_rn(S, __shfl_sync(0xffffffffu, p[j], l));
   }
   return S;
 }
@@ -603,14 +608,23 @@ __device__ __forceinline__ double walk_chunks(const double2 *__restrict__ state,
                                               const unsigned char *__restrict__ flag,
                                               int have_deltas, double *__restrict__ exact, double S,
                                               int lane, long long &n_replay) {
+  double nx_d = 0.0, nx_a = 0.0;
+  int nx_f = FLAG_CROSS;
+  if (have_deltas && c_begin + lane < c_end) {
+    nx_d = delta[c_begin + lane];
+    nx_a = approx[c_begin + lane];
+    nx_f = flag[c_begin + lane];
+  }
   for (uint64_t base = c_begin; base < c_end; base += 32) {
     const uint64_t mine = base + lane;
-    double my_d = 0.0, my_a = 0.0;
-    int my_f = FLAG_CROSS;
-    if (have_deltas && mine < c_end) {
-      my_d = delta[mine];
-      my_a = approx[mine];
-      my_f = flag[mine];
+    const double my_d = nx_d, my_a = nx_a;
+    const int my_f = nx_f;
+    // the next block's records are fetched while this one is processed (one warp walks alone here)
+    nx_d = 0.0; nx_a = 0.0; nx_f = FLAG_CROSS;
+    if (have_deltas && mine + 32 < c_end) {
+      nx_d = delta[mine + 32];
+      nx_a = approx[mine + 32];
+      nx_f = flag[mine + 32];
     }
     double my_exact = 0.0;
     const int lim = (int)((c_end - base) < 32 ? (c_end - base) : 32);
