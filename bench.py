@@ -499,6 +499,7 @@ def main() -> None:
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    step_ms = []
     phase_s = {"qc_create": 0.0, "gates + qc_find_most_likely_state": 0.0, "qc_get_probability": 0.0, "qc_destroy": 0.0}
     for _ in range(e2e_steps):
         ta = time.perf_counter()
@@ -514,6 +515,7 @@ def main() -> None:
         te = time.perf_counter()
         for key, dt in zip(phase_s, (tb - ta, tc - tb, td - tc, te - td)):
             phase_s[key] += dt
+        step_ms.append(1e3 * (te - ta))
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -622,6 +624,7 @@ def main() -> None:
         "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": h2d_per_step,
                 "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps,
                 "host_ms_per_step_by_call": {k2: 1e3 * v / e2e_steps for k2, v in phase_s.items()},
+                "host_ms_of_each_step": [round(v, 2) for v in step_ms],
                 "what": "qc_create + qc_quantum_fourier_transform + qc_find_most_likely_state + "
                         "qc_get_probability + qc_destroy through libqcs.so"},
         "gpu_launches": st["kernel_launches"],

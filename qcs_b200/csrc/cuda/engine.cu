@@ -572,7 +572,7 @@ static bool can_fuse_swaps(const Engine &e) {
   if (!e.opt.fusion || e.nl < min_tile_bits(e) || e.opt.sem != SEM_CORRECTED || e.opt.exchange != 1 ||
       !e.opt.fuse_swaps)
     return false;
-  if (e.opt.tile_kernel != 0 && e.opt.tile_kernel != 3) return false;
+  if (e.opt.tile_kernel != 3) return false;  // the remap machinery is compiled into the ldg8 kernels only
   return e.opt.dryrun ? dist().active : (dist_p2p_available(e) && e.tile_flags != nullptr);
 }
 

@@ -209,6 +209,7 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 // ---------------------------------------------------------------------------
 // Kernel bodies, instantiated for R = 4 (16 amplitudes/thread) and R = 3 (8).
 // ---------------------------------------------------------------------------
+#define QCS_SWAP 0
 #define QCS_FAST 0
 #define QCS_R 4
 #define QCS_CT (1 << (QCS_T - QCS_R))
@@ -269,6 +270,35 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 #undef QCS_NAME
 #undef QCS_WITH_TMA
 
+// the same three shapes once more with the remap machinery compiled in (QCS_SWAP): x_r3s...
+#define QCS_WITH_TMA 0
+#undef QCS_SWAP
+#define QCS_SWAP 1
+#define QCS_T 12
+#define QCS_MIN_CTAS 2
+#define QCS_NAME(x) x##_r3s
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+#define QCS_T 11
+#define QCS_MIN_CTAS 4
+#define QCS_NAME(x) x##_r3s_t11
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+#define QCS_T 10
+#define QCS_MIN_CTAS 8
+#define QCS_NAME(x) x##_r3s_t10
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+#undef QCS_SWAP
+#define QCS_SWAP 0
+#undef QCS_WITH_TMA
+
 #define QCS_T 11
 #define QCS_MIN_CTAS 4
 #define QCS_NAME(x) x##_r3_t11
@@ -317,6 +347,32 @@ __device__ __forceinline__ void bulk_store(void *dst, uint32_t src_smem, uint32_
 #undef QCS_T
 #undef QCS_MIN_CTAS
 #undef QCS_NAME
+
+#undef QCS_SWAP
+#define QCS_SWAP 1
+#define QCS_T 12
+#define QCS_MIN_CTAS 2
+#define QCS_NAME(x) x##_r3fs
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+#define QCS_T 11
+#define QCS_MIN_CTAS 4
+#define QCS_NAME(x) x##_r3fs_t11
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+#define QCS_T 10
+#define QCS_MIN_CTAS 8
+#define QCS_NAME(x) x##_r3fs_t10
+#include "fused_body.inc"
+#undef QCS_T
+#undef QCS_MIN_CTAS
+#undef QCS_NAME
+#undef QCS_SWAP
+#define QCS_SWAP 0
 #undef QCS_WITH_TMA
 
 #undef QCS_R
@@ -377,6 +433,14 @@ static int tile_row_bits(const PassParams &p) {
 using LdgKernel = void (*)(double2 *, const PassParams, uint32_t, const SwapStore, const PassExtras, uint32_t);
 
 // [math=fast][16 amplitudes per thread][tile bits - 10]
+// the ldg8 shapes with the remap machinery compiled in: [math=fast][tile bits - 10]
+static LdgKernel ldg8_remap_kernel(bool fast, int T) {
+  static const LdgKernel table[2][3] = {
+      {fused_pass_ldg_r3s_t10, fused_pass_ldg_r3s_t11, fused_pass_ldg_r3s},
+      {fused_pass_ldg_r3fs_t10, fused_pass_ldg_r3fs_t11, fused_pass_ldg_r3fs}};
+  return table[fast ? 1 : 0][T - QCS_MIN_TILE_BITS];
+}
+
 static LdgKernel ldg_kernel(bool fast, bool r4, int T) {
   static const LdgKernel table[2][2][3] = {
       {{fused_pass_ldg_r3_t10, fused_pass_ldg_r3_t11, fused_pass_ldg_r3},
@@ -390,6 +454,7 @@ static LdgKernel ldg_kernel(bool fast, bool r4, int T) {
 struct DeviceLaunchState {
   int sm_count = 0;
   bool ldg_configured[2][2][3] = {};
+  bool remap_configured[2][3] = {};
   bool tma_configured[2] = {false, false};
 };
 static DeviceLaunchState *device_launch_state(cudaError_t *err) {
@@ -423,6 +488,7 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
   if (variant < 0 || variant > 3) return cudaErrorInvalidValue;
   const bool ldg = variant == 0 || variant == 3;
   if ((swap || fast || pass_flags) && !ldg) return cudaErrorInvalidValue;  // plain-load kernels only
+  if (swap && swap->k && variant != 3) return cudaErrorInvalidValue;        // remaps ride on ldg8 passes only
   SwapStore sw{};
   if (swap) sw = *swap;
   PassExtras ex{};
@@ -441,8 +507,10 @@ cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_lo
     const bool r4 = variant == 0;
     // math=fast: the tile + one 16-byte factor per uniform fan behind it
     const size_t smem = ((size_t)16 << T) + (fast ? 16 * QCS_MAX_PASS_FANS : 0);
-    LdgKernel k = ldg_kernel(fast, r4, T);
-    bool &configured = dls->ldg_configured[fast ? 1 : 0][r4 ? 1 : 0][T - QCS_MIN_TILE_BITS];
+    const bool remap = swap && sw.k;
+    LdgKernel k = remap ? ldg8_remap_kernel(fast, T) : ldg_kernel(fast, r4, T);
+    bool &configured = remap ? dls->remap_configured[fast ? 1 : 0][T - QCS_MIN_TILE_BITS]
+                             : dls->ldg_configured[fast ? 1 : 0][r4 ? 1 : 0][T - QCS_MIN_TILE_BITS];
     if (!configured) {
       e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;

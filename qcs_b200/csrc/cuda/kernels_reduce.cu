@@ -374,6 +374,16 @@ __device__ __forceinline__ double masked_norm(const double2 *__restrict__ state,
   if (mask_pos >= 0 && ((i >> mask_pos) & 1ull)) return 0.0;
   return norm_sq(__ldg(state + i));
 }
+// The same from an amplitude already in registers.  Kernels that are short of warps (one warp per 32
+// chunks, or one warp in all) fetch a batch of amplitudes with back-to-back loads first and turn them
+// into terms afterwards: with masked_norm's branches between the loads the compiler serialises them,
+// one memory latency per term (the 24-qubit Grover search spent 0.57 of its 1.3 ms per iteration
+// that way, profiles/r2l_launches_grover24.csv).
+__device__ __forceinline__ double term_of(double2 a, uint64_t i, int mask_pos) {
+  if (mask_pos <= SEL_RE) return mask_pos == SEL_RE ? a.x : a.y;
+  const double p = norm_sq(a);
+  return (mask_pos >= 0 && ((i >> mask_pos) & 1ull)) ? 0.0 : p;
+}
 
 // K1: plain (tree) sum of each 1024-term chunk; one warp per chunk.
 __global__ void __launch_bounds__(256)
@@ -502,12 +512,17 @@ chunk_delta_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mas
   for (int j = 0; j < SEQ_CHUNK / 32; j++) {
     // all 32 row loads of this step are issued before the first is used: on small shards (a 24-qubit
     // Grover search has 512 warps in this kernel) nothing else hides their latency
-    double pv[32];
+    double2 raw[32];
 #pragma unroll
-    for (int c = 0; c < 32; c++)
-      pv[c] = c < n_rows ? masked_norm(state, (c0 + c) * SEQ_CHUNK + (uint64_t)j * 32 + lane, mask_pos) : 0.0;
+    for (int c = 0; c < 32; c++) {
+      const uint64_t i = (c0 + (uint64_t)(c < n_rows ? c : 0)) * SEQ_CHUNK + (uint64_t)j * 32 + lane;
+      raw[c] = __ldg(state + i);  // rows past the end re-read row 0 (discarded below): no branch between the loads
+    }
 #pragma unroll
-    for (int c = 0; c < 32; c++) stage[wib][c][lane] = pv[c];
+    for (int c = 0; c < 32; c++) {
+      const uint64_t i = (c0 + c) * SEQ_CHUNK + (uint64_t)j * 32 + lane;
+      stage[wib][c][lane] = c < n_rows ? term_of(raw[c], i, mask_pos) : 0.0;
+    }
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < 32; k++) {
@@ -542,11 +557,17 @@ chunk_delta_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mas
 // past `len` contribute +0.0 (S + 0.0 == S).
 __device__ __forceinline__ double replay_chunk(const double2 *__restrict__ state, uint64_t first,
                                                uint64_t len, int mask_pos, double S, int lane) {
+  double2 raw[SEQ_CHUNK / 32];
+#pragma unroll
+  for (int j = 0; j < SEQ_CHUNK / 32; j++) {
+    const uint64_t off = (uint64_t)j * 32 + lane;
+    raw[j] = __ldg(state + first + (off < len ? off : 0));  // no branch between the loads
+  }
   double p[SEQ_CHUNK / 32];
 #pragma unroll
   for (int j = 0; j < SEQ_CHUNK / 32; j++) {
     const uint64_t off = (uint64_t)j * 32 + lane;
-    p[j] = off < len ? masked_norm(state, first + off, mask_pos) : 0.0;
+    p[j] = off < len ? term_of(raw[j], first + off, mask_pos) : 0.0;
   }
 #pragma unroll
   for (int j = 0; j < SEQ_CHUNK / 32; j++) {

@@ -25,6 +25,6 @@ for label, kw, first in cases:
             c.find_most_likely_state(); t.append(time.perf_counter())
         c.close(); t.append(time.perf_counter())
         names = ["create", "submit", "first_read", "second_read", "destroy"]
-        if rep:
+        if True:
             print(f"{label:32s}", {k: round((t[i + 1] - t[i]) * 1e3, 2) for i, k in enumerate(names)},
                   "total", round((t[-1] - t[0]) * 1e3, 2), flush=True)
