@@ -41,9 +41,11 @@ enum {
 };
 
 /* ---- storage: q_state_init / q_state_free (reference src/q_state.c:32-115) -- */
-/* Allocates the device-resident amplitude buffer(s), zeroes them and sets
- * amplitude 0 to 1.  With a communicator installed (qcs_cuda_dist_init) the
- * state is sharded on its top log2(world) qubits and this rank holds one shard. */
+/* Allocates the device-resident amplitude buffer(s); the state is |0...0> (the
+ * reference zeroes the vector and sets amplitude 0 to 1; here the bytes are written
+ * lazily -- the first fused pass synthesises its input -- unless "lazy_init" = off).
+ * With a communicator installed (qcs_cuda_dist_init) the state is sharded on its
+ * top log2(world) qubits and this rank holds one shard. */
 int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits);
 void qcs_cuda_state_destroy(qcs_cuda_engine *e);
 
@@ -55,7 +57,12 @@ int qcs_cuda_apply_c1q(qcs_cuda_engine *e, const double m[8], int control,
                        int target);
 /* q_apply_phase_flip (reference src/q_gates.c:305-317). */
 int qcs_cuda_phase_flip(qcs_cuda_engine *e, long index);
-/* q_apply_diffusion (reference src/q_gates.c:323-356). */
+/* q_apply_diffusion (reference src/q_gates.c:323-356).  The mean is built from the
+ * reference's left-to-right sums of the real and of the imaginary parts, replayed
+ * exactly on the device (math=exact: every amplitude of a Grover search equals the
+ * reference's; math=fast uses a tree sum, which is closer to the exact mean than the
+ * reference's drifting sequential sum and therefore NOT within 1e-12 of it on large
+ * registers). */
 int qcs_cuda_diffusion(qcs_cuda_engine *e);
 /* q_state_normalize (reference src/q_utils.c:44-119). */
 int qcs_cuda_normalize(qcs_cuda_engine *e);
@@ -110,7 +117,10 @@ int qcs_cuda_write_amplitudes(qcs_cuda_engine *e, int which, long first,
  *   runs of controlled phases merged into one factor, commuting gates scheduled out of order; amplitudes
  *   then agree with the reference within 1e-12 relative),
  * "reorder" = on|off, "reorder_segments" = 1..12 (math=fast: commutation-aware scheduling and how many
- *   segments a reordered pass may spend).
+ *   segments a reordered pass may spend),
+ * "lazy_init" = on|off, "fuse_argmax" = on|off (qc_find_most_likely_state behind queued gates takes one
+ *   candidate per tile from the flush's last pass), "swap_store" = bulk|thread, "remap_max" = 1..3
+ *   (position pairs one carrying pass may trade), "victim_policy" = mru|lru (INTEGRATION.md lists all keys).
  * Defaults come from QCS_CUDA_<KEY> in the environment; set_default applies
  * to engines created afterwards. */
 int qcs_cuda_set_default(const char *key, const char *value);

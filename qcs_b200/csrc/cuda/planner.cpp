@@ -462,11 +462,26 @@ struct PassBuilder {
                  gates[gi + run].tpos == g.tpos && run < QCS_MAX_FAN_ENTRIES)
             run++;
           if (run >= 2 && !cfg.fast_math) {
-            bool consecutive = true;
-            for (int k = 1; k < run; k++)
-              if (gates[gi + k].cpos != g.cpos + k) consecutive = false;
-            emit_fan_header(g, run, consecutive, false);
-            for (int k = 0; k < run; k++) emit_record(gates[gi + k]);
+            // The fast walk needs entry k to be controlled by position cpos + k (the thread's mask is one
+            // shift of its basis index); any other order makes the kernel gather the mask entry by
+            // entry, ~10 instructions each.  On a sharded engine the layout drifts (after a remap
+            // logical qubit 30 may sit below qubit 29), so a QFT's run of controls 3..30 stops being
+            // ascending at its very end: the whole 28-entry fan fell back to the gather and the first
+            // QFT pass took 39.5 instead of 31 ms (profiles/r2j_bench_2gpu.json).  Order must be kept
+            // (bit-exactness), so the run is cut where it stops ascending by one: every ascending
+            // stretch of two or more entries is a consecutive fan, a stretch of one an ordinary gate.
+            int k0 = 0;
+            while (k0 < run) {
+              int len = 1;
+              while (k0 + len < run && gates[gi + k0 + len].cpos == gates[gi + k0].cpos + len) len++;
+              if (len >= 2 && n_fans + 1 <= QCS_MAX_PASS_FANS) {
+                emit_fan_header(gates[gi + k0], len, true, false);
+                for (int k = 0; k < len; k++) emit_record(gates[gi + k0 + k]);
+              } else {
+                for (int k = 0; k < len; k++) emit_record(gates[gi + k0 + k]);
+              }
+              k0 += len;
+            }
             gi += run - 1;
             continue;
           }
@@ -478,6 +493,12 @@ struct PassBuilder {
             std::vector<int> own, shared;
             for (int k = 0; k < run; k++)
               (tilebit_of(gates[gi + k].cpos) >= 0 ? own : shared).push_back(gi + k);
+            // (the entries commute and the mode merges their phases anyway: sorted by control position
+            // the shift-based mask applies whenever the positions are contiguous, whatever order the
+            // circuit -- or a drifted layout -- listed them in)
+            auto by_cpos = [&](int a, int b) { return gates[a].cpos < gates[b].cpos; };
+            std::sort(own.begin(), own.end(), by_cpos);
+            std::sort(shared.begin(), shared.end(), by_cpos);
             for (int part = 0; part < 2; part++) {
               const std::vector<int> &ids = part == 0 ? own : shared;
               if (ids.size() >= 2) {
