@@ -183,6 +183,10 @@ long qcs_cuda_describe_last_plan(qcs_cuda_engine *e, char *buf, long cap);
  * into buf (when cap is large enough); returns the number of passes of the last flush.  Lets a
  * CPU test interpret exactly what the GPU would be handed (tests/test_planner.py). */
 long qcs_cuda_last_plan_raw(qcs_cuda_engine *e, long pass_index, void *buf, long cap);
+/* math=fast: the thread-table fans that travel next to pass `pass_index` (PassParams::n_thread_tables
+ * tables of 2^(tile_bits - reg_bits) complex numbers {re, im}, common.h QCS_OP_TFAN_BASE), copied into
+ * buf when cap (in doubles) is large enough; returns their size in doubles. */
+long qcs_cuda_last_plan_tables(qcs_cuda_engine *e, long pass_index, double *buf, long cap);
 /* Sharded engines: how many (local position, global position) pairs entry `pass_index` of the last
  * flush trades -- all at once on the stores of that pass (a remap of up to 3 pairs: an all-to-all
  * among 2^k ranks), or (plan-only engines list these too, as entries with no segments) as a

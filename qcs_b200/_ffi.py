@@ -70,6 +70,7 @@ CUDA_ABI = {
     "qcs_cuda_pass_descriptor_bytes": (_L, []),
     "qcs_cuda_describe_last_plan": (_L, [_P, ctypes.c_char_p, _L]),
     "qcs_cuda_last_plan_raw": (_L, [_P, _L, ctypes.c_void_p, _L]),
+    "qcs_cuda_last_plan_tables": (_L, [_P, _L, _DP, _L]),
     "qcs_cuda_last_plan_swap": (_L, [_P, _L, _IP, _IP]),
     "qcs_cuda_last_plan_pass_info": (_L, [_P, _L, _DP, _DP, _IP, _IP]),
     "qcs_cuda_last_error": (ctypes.c_char_p, []),

@@ -44,7 +44,8 @@ enum GateFlags : uint8_t {
   GF_ROW0_ONLY = 1,   // reference-semantics controlled gate: only the target=0 row is written
   GF_D0_IDENT = 2,    // diagonal entry 0 is exactly (1,0): untouched
   GF_D1_IDENT = 4,    // diagonal entry 1 is exactly (1,0): untouched
-  GF_FAN_HEADER = 0x80  // not a gate: header record of a controlled-phase fan (below)
+  GF_TFAN_HEADER = 0x40,  // not a gate: header record of a thread-table fan (QCS_OP_TFAN_BASE below)
+  GF_FAN_HEADER = 0x80    // not a gate: header record of a controlled-phase fan (below)
 };
 
 // Dispatch ids.  The formulas below give SYMBOLIC ids; DGate.op holds the case label the generator
@@ -78,6 +79,17 @@ static inline int qcs_op_id_diag_reg(int treg, int creg, int halves) {
 // slot `csel`; the interpreter fetches it with one ld.shared.  PassParams::ufan_header lists the
 // headers.  (QFT: 20 of the 29 controls of the first target are outside a 10-bit tile.)
 #define QCS_OP_UFAN_BASE 248
+// math=fast only.  Header of a THREAD-TABLE fan, op = QCS_OP_TFAN_BASE + treg + 1.  The entries of a run of
+// controlled phases on one target whose controls are tile positions that are not register bits (lane and
+// warp bits) multiply a thread's amplitudes by a product that depends on the thread's lane / warp bits
+// only -- the same CT numbers for every CTA of the pass.  The planner builds that table on the host
+// (PassPlan::thread_tables, table `tsel`, one complex per thread id; the engine uploads it next to the
+// pass), the kernel fetches its entry with one coalesced load, multiplies it with the per-CTA factor of
+// the run's out-of-tile controls (uniform-fan slot `csel`, 0xFF: none) and applies the product once.
+// pad[1] = records behind the header that the kernel skips: pad[2] own entries (ordinary records, kept
+// so that a plan can be read back -- and checked -- gate by gate) and, when csel != 0xFF, the uniform
+// fan's header and entries (listed in ufan_header for the prologue, never dispatched).
+#define QCS_OP_TFAN_BASE 235
 // or-ed into a pairing / diagonal id: the gate's control is a bit the thread tests once for all its
 // amplitudes (a lane / warp tile bit, a position outside the tile, a rank bit); csel = its position
 #define QCS_OP_TCTL 0x100
@@ -102,7 +114,8 @@ struct DGate {
 static_assert(sizeof(DGate) == 80, "DGate layout is part of the generated interpreter");
 static_assert(__builtin_offsetof(DGate, op) == 64 && __builtin_offsetof(DGate, csel) == 66 &&
               __builtin_offsetof(DGate, tsel) == 67 && __builtin_offsetof(DGate, tpos) == 70 &&
-              __builtin_offsetof(DGate, cpos) == 71, "DGate layout is part of the generated interpreter");
+              __builtin_offsetof(DGate, cpos) == 71 && __builtin_offsetof(DGate, pad) == 73,
+              "DGate layout is part of the generated interpreter");
 
 struct DSegment {
   // role r -> tile bit index; roles 0-4 lane bits, then warp bits, the last reg_bits are register bits
@@ -139,5 +152,5 @@ struct PassParams {
   // shared-memory factor table belongs to ufan_header[k]
   uint16_t ufan_header[QCS_MAX_PASS_FANS];
   int32_t n_ufans;
-  int32_t pad_;
+  int32_t n_thread_tables;             // math=fast: tables of 2^(tile_bits - reg_bits) complex numbers behind the pass
 };

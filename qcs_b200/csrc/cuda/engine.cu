@@ -97,6 +97,9 @@ static int load_options(Options &o) {
   else return set_error(QCS_CUDA_ERR_INVALID, "exchange must be p2p|nccl, got '%s'", v.c_str());
   v = option_value("fuse_swaps");
   o.fuse_swaps = !(v == "off" || v == "0");
+  v = option_value("fan_tables");
+  // "off" | "on" | the fewest in-tile controls a run needs to become a table (on = 2)
+  o.fan_tables = (v == "off" || v == "0") ? 0 : (v.empty() || v == "on") ? 2 : std::max(2, std::atoi(v.c_str()));
   v = option_value("victim_policy");
   if (v == "lru") o.victim_policy = 0;
   else if (v.empty() || v == "mru") o.victim_policy = 1;
@@ -353,6 +356,7 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
   // (sharded engines: run_range_reordered keeps track of which gates a pass took)
   cfg.reorder = e.opt.fast_math && e.opt.reorder;
   cfg.reorder_segments = e.opt.reorder_segments;
+  cfg.thread_tables = e.opt.fan_tables;
   cfg.tile_bits_min = min_tile_bits(e);
   cfg.tile_bits_max = std::max(cfg.tile_bits_min, std::min(e.opt.tile_bits, e.nl));
   return plan_passes(gates, cfg);
@@ -390,6 +394,17 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
       e.argmax_done = true;
       e.argmax_tiles = e.local_size >> p.params.tile_bits;
     }
+    if (!e.opt.dryrun && !p.thread_tables.empty()) {
+      // math=fast: the pass's thread-table fans.  One device buffer serves every pass: the copy is ordered
+      // on the stream behind the previous pass's kernel (the source is pageable host memory, staged by the
+      // driver before cudaMemcpyAsync returns, so `plan` may die before the copy runs)
+      const size_t cap = (size_t)QCS_MAX_PASS_FANS * sizeof(double2) << (QCS_TILE_BITS - 3);
+      if (!e.table_buf) CK(cudaMalloc((void **)&e.table_buf, cap));
+      const size_t bytes = p.thread_tables.size() * sizeof(double);
+      if (bytes > cap) return set_error(QCS_CUDA_ERR_CUDA, "internal: thread tables exceed their buffer");
+      CK(cudaMemcpyAsync(e.table_buf, p.thread_tables.data(), bytes, cudaMemcpyHostToDevice, e.stream));
+      extras.thread_tables = e.table_buf;
+    }
     if (!e.opt.dryrun) {
       if (carries) {
         SwapStore sw = *swap;
@@ -417,7 +432,7 @@ static int launch_passes(Engine &e, const std::vector<PassPlan> &plan, size_t fi
         sw.bulk = e.opt.swap_bulk ? 1u : 0u;
         sw.row_bits = 0;
         while (sw.row_bits < (uint32_t)p.params.tile_bits && p.params.tile_pos[sw.row_bits] == sw.row_bits) sw.row_bits++;
-        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, &sw, e.opt.fast_math, pass_flags));
+        CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, &sw, e.opt.fast_math, pass_flags, &extras));
         RC(dist_after_fused_swap(e));
       } else {
         CK(launch_fused_pass(e.live, p.params, e.nl, e.stream, e.opt.tile_kernel, nullptr, e.opt.fast_math, pass_flags, &extras));
@@ -1146,6 +1161,7 @@ void qcs_cuda_state_destroy(qcs_cuda_engine *e) {
   pool_free(e->ws_slab, e->ws_slab_bytes);
   cudaFree(e->u_dev);
   cudaFree(e->idx_dev);
+  cudaFree(e->table_buf);
   pool_free(e->argmax_tile_p, (e->local_size >> QCS_MIN_TILE_BITS) * sizeof(double));
   pool_free(e->argmax_tile_idx, (e->local_size >> QCS_MIN_TILE_BITS) * sizeof(long long));
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -1626,6 +1642,13 @@ long qcs_cuda_last_plan_pass_info(qcs_cuda_engine *e, long pass_index, double *m
   if (tile_bits) *tile_bits = p.params.tile_bits;
   if (segments) *segments = p.params.n_segments;
   return (long)e->last_plan.size();
+}
+
+long qcs_cuda_last_plan_tables(qcs_cuda_engine *e, long pass_index, double *buf, long cap) {
+  if (!e || pass_index < 0 || pass_index >= (long)e->last_plan.size()) return 0;
+  const std::vector<double> &t = e->last_plan[(size_t)pass_index].thread_tables;
+  if (buf && cap >= (long)t.size() && !t.empty()) std::memcpy(buf, t.data(), t.size() * sizeof(double));
+  return (long)t.size();
 }
 
 long qcs_cuda_last_plan_raw(qcs_cuda_engine *e, long pass_index, void *buf, long cap) {

@@ -35,6 +35,8 @@ struct Options {
   int reorder_segments = 8;
   bool peephole = true;    // drop exactly self-cancelling gate pairs from the queue (corrected semantics)
   bool fuse_swaps = true;  // fold position swaps into the stores of a pass (peer-memory path only)
+  int fan_tables = 2;  // math=fast: runs of controlled phases with at least this many in-tile controls become
+                       // per-thread tables (0 = never)
   int victim_policy = 1;   // which local position leaves when the queue pairs none of the candidates again:
                            // 1 the most recently paired (cyclic sweeps), 0 the least recently paired
   int remap_max = 3;       // position pairs one carrying pass may trade (1..3): an all-to-all among 2^k ranks
@@ -93,6 +95,7 @@ struct Engine {
   ReduceWorkspace ws{};
   void *ws_slab = nullptr;       // one allocation backing every array of ws
   size_t ws_slab_bytes = 0;
+  double2 *table_buf = nullptr;   // math=fast: thread-table fans of the pass about to run (device)
   double *u_dev = nullptr;
   long long *idx_dev = nullptr;
   int shots_cap = 0;

@@ -35,6 +35,7 @@ OFF_M = lambda i: 8 * i       # noqa: E731  m[i]
 OFF_W0 = 64                   # op (u16) | csel << 16 | tsel << 24
 OFF_TPOS = 70
 OFF_CPOS = 71
+OFF_PAD1 = 74                 # pad[1]: thread-table fans, records to skip behind the header
 SIZEOF_DGATE = 80
 
 SYM_NOP = 255
@@ -359,6 +360,34 @@ def emit(R, fast=False):
             continue
         body = ["bfe.u32 K, w0, 24, 8;", "bfe.u32 c0, w0, 16, 8;", "add.s32 %0, %0, K;",
                 "mad.lo.u32 c0, c0, 16, ufb;", "ld.shared.v2.f64 {ar, ai}, [c0];"]
+        if t < 0:
+            body += [f"ld.param.u8 cs, [%1+{OFF_TPOS}];", "shr.u64 t64, %2, cs;", "and.b64 t64, t64, 1;",
+                     "setp.eq.u64 p, t64, 0;", "@p bra DONE;"]
+            body += acc_thread_factor("ar", "ai")
+        else:
+            for r in regs(R, t, 1):
+                body += op_diag_fast(r, "ar", "ai")
+        blocks.append((new_case(sym), body + ["bra DONE;"]))
+    # thread-table fan (id 235 + treg + 1, math=fast only; common.h QCS_OP_TFAN_BASE): the product of the
+    # phases of the in-tile controls this thread has set comes out of a host-built table -- one load, the
+    # threads of a warp read consecutive entries -- times the per-CTA factor of the out-of-tile controls
+    # (uniform-fan slot csel, 0xFF = none).  tfb (named 64-bit register, set once per CTA) = address of
+    # this thread's entry of table 0, tfs = bytes per table.  pad[1] records behind the header are skipped.
+    for t in range(-1, R):
+        sym = 235 + t + 1
+        n = f"{t + 1}"
+        if not fast:
+            blocks.append((new_case(sym), ["bra DONE;"]))
+            continue
+        body = [f"ld.param.u8 cs, [%1+{OFF_PAD1}];", "add.s32 %0, %0, cs;",
+                "bfe.u32 K, w0, 24, 8;", "bfe.u32 c0, w0, 16, 8;",
+                "mul.wide.u32 ea, K, tfs;", "add.u64 ea, ea, tfb;",
+                "ld.global.nc.v2.f64 {ar, ai}, [ea];",
+                "setp.eq.u32 p, c0, 255;", f"@p bra TA{n};",
+                "mad.lo.u32 c0, c0, 16, ufb;", "ld.shared.v2.f64 {dr, di}, [c0];",
+                "mul.rn.f64 t0, ai, di;", "mul.rn.f64 t1, ai, dr;", "neg.f64 t0, t0;",
+                "fma.rn.f64 t2, ar, dr, t0;", "fma.rn.f64 ai, ar, di, t1;", "mov.f64 ar, t2;",
+                f"TA{n}:"]
         if t < 0:
             body += [f"ld.param.u8 cs, [%1+{OFF_TPOS}];", "shr.u64 t64, %2, cs;", "and.b64 t64, t64, 1;",
                      "setp.eq.u64 p, t64, 0;", "@p bra DONE;"]

@@ -53,6 +53,7 @@ enum { QCS_PASS_SYNTH_ZERO_KET = 1, QCS_PASS_ARGMAX = 2 };
 struct PassExtras {
   double *argmax_p;
   long long *argmax_idx;
+  const double2 *thread_tables;  // math=fast: the pass's thread-table fans (common.h QCS_OP_TFAN_BASE), device memory
 };
 cudaError_t launch_fused_pass(double2 *state, const PassParams &params, int n_local,
                               cudaStream_t stream, int variant, const SwapStore *swap = nullptr,

@@ -499,6 +499,65 @@ struct PassBuilder {
             auto by_cpos = [&](int a, int b) { return gates[a].cpos < gates[b].cpos; };
             std::sort(own.begin(), own.end(), by_cpos);
             std::sort(shared.begin(), shared.end(), by_cpos);
+            // Thread-table fan (common.h QCS_OP_TFAN_BASE): what the own entries do to a thread depends
+            // on its lane and warp bits only, so the product of their phases over the controls a
+            // thread has set is tabulated here, once for every CTA of the pass: one coalesced load per
+            // thread replaces the walk over product tables (per-thread constant loads and ~25
+            // instructions per group of four entries -- most of the first QFT pass's instructions).
+            const bool table = cfg.thread_tables >= 2 && (int)own.size() >= cfg.thread_tables && pp.n_thread_tables < QCS_MAX_PASS_FANS &&
+                               n_fans + 2 <= QCS_MAX_PASS_FANS && out_n + 2 + run <= QCS_MAX_PASS_GATES + QCS_MAX_PASS_FANS;
+            if (table) {
+              const int CT = 1 << (T - cfg.reg_bits);
+              const int treg = reg_of(g.tpos);
+              const int h = out_n;
+              DGate &hd = pp.gate[out_n++];
+              std::memset(&hd, 0, sizeof(hd));
+              hd.op = case_label(QCS_OP_TFAN_BASE + treg + 1);
+              hd.kind = GK_DIAG;
+              hd.flags = GF_TFAN_HEADER;
+              hd.tsel = (uint8_t)pp.n_thread_tables;
+              hd.csel = shared.size() >= 2 ? (uint8_t)pp.n_ufans : 0xFF;  // the uniform fan emitted below gets this slot
+              hd.tpos = (int8_t)g.tpos;
+              hd.cpos = -1;
+              hd.treg_creg = (uint8_t)(treg + 1);
+              hd.pad[2] = (uint8_t)own.size();
+              n_fans++;
+              // W[tid] = product of the phases of the own entries whose control bit thread tid has set
+              // (tid -> tile index through the segment's role tables, exactly as the kernel maps it)
+              const size_t base = plan.thread_tables.size();
+              plan.thread_tables.resize(base + 2 * (size_t)CT);
+              for (int tid = 0; tid < CT; tid++) {
+                uint32_t tb = 0;
+                for (int role = 0; role < T - cfg.reg_bits; role++)
+                  if ((tid >> role) & 1) tb |= 1u << ds.role_tilebit[role];
+                long double re = 1.0L, im = 0.0L;
+                for (int id : own) {
+                  const int cb = tilebit_of(gates[id].cpos);
+                  if (!((tb >> cb) & 1u)) continue;
+                  const long double pr = gates[id].c.m[6], pi = gates[id].c.m[7];
+                  const long double nre = re * pr - im * pi, nim = re * pi + im * pr;
+                  re = nre;
+                  im = nim;
+                }
+                plan.thread_tables[base + 2 * (size_t)tid] = (double)re;
+                plan.thread_tables[base + 2 * (size_t)tid + 1] = (double)im;
+              }
+              pp.n_thread_tables++;
+              for (int id : own) emit_record(gates[id]);
+              if (shared.size() >= 2) {
+                bool consecutive = true;
+                for (size_t k = 1; k < shared.size(); k++)
+                  if (gates[shared[k]].cpos != gates[shared[0]].cpos + (int)k) consecutive = false;
+                emit_fan_header(gates[shared[0]], (int)shared.size(), consecutive, true);
+                for (int id : shared) emit_record(gates[id]);
+                pp.gate[h].pad[1] = (uint8_t)(own.size() + 1 + shared.size());
+              } else {
+                pp.gate[h].pad[1] = (uint8_t)own.size();
+                for (int id : shared) emit_record(gates[id]);  // a single out-of-tile control: an ordinary gate
+              }
+              gi += run - 1;
+              continue;
+            }
             for (int part = 0; part < 2; part++) {
               const std::vector<int> &ids = part == 0 ? own : shared;
               if (ids.size() >= 2) {
@@ -785,6 +844,11 @@ std::string describe_plan(const std::vector<PassPlan> &passes) {
         const DGate &g = pp.gate[gi];
         if (g.flags & GF_FAN_HEADER) {
           std::snprintf(buf, sizeof(buf), " fan[%d]", (int)g.tsel);
+          s += buf;
+          continue;
+        }
+        if (g.flags & GF_TFAN_HEADER) {
+          std::snprintf(buf, sizeof(buf), " tfan[%d]", (int)g.pad[2]);
           s += buf;
           continue;
         }

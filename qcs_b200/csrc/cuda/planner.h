@@ -47,6 +47,9 @@ struct PassPlan {
                             // on its stores, all at once (params.n_segments == 0: a stand-alone swap, no pass)
   double flops_per_amp;     // planner's cost estimate
   std::vector<int> tile_positions;
+  // math=fast: params.n_thread_tables tables of 2^(tile_bits - reg_bits) complex numbers {re, im}
+  // (common.h QCS_OP_TFAN_BASE); the engine copies them to the device in front of the launch
+  std::vector<double> thread_tables;
 };
 
 struct PlannerConfig {
@@ -66,6 +69,8 @@ struct PlannerConfig {
                             // target of both) may trade places, so a pass is a SUBSEQUENCE of the queue
                             // chosen to keep a tile busy over several circuit layers (plan_passes_reordered)
   int reorder_segments = 8; // segments a reordered pass may spend before the next pass starts
+  int thread_tables = 2;  // math=fast: runs of controlled phases with in-tile controls become one table
+                            // lookup per thread (common.h QCS_OP_TFAN_BASE) instead of a walk over product tables
   int fixed_low = QCS_LANE_BITS;  // positions 0..fixed_low-1 belong to every tile: global rows of
                             // 16 << fixed_low contiguous bytes; the remaining tile bits are free
 };

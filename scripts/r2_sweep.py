@@ -1,6 +1,6 @@
 """Round-2 kernel sweep: every plain-load tile kernel shape (8 or 16 amplitudes per thread, 10/11/12-bit
 tiles) on the workloads of BASELINE configs 3 and 5, bit-exact and math=fast (development aid;
-bench.py is the contract).   usage: r2_sweep.py [qubits] [what,...]"""
+bench.py is the contract).   usage: r2_sweep.py [qubits] [what,...] [math,...] [shape,...] [option=value,...]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qcs_b200 import Circuit
@@ -36,11 +36,15 @@ def run(n, script, label, reps=3, **kw):
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 what = sys.argv[2].split(",") if len(sys.argv) > 2 else ["qft", "random", "rz", "h"]
+maths = sys.argv[3].split(",") if len(sys.argv) > 3 and sys.argv[3] else ["exact", "fast"]
 shapes = [("ldg8", 10), ("ldg8", 11), ("ldg", 10), ("ldg", 11), ("ldg", 12)]
-for math in ("exact", "fast"):
+if len(sys.argv) > 4 and sys.argv[4]:
+    shapes = [(s.split(":")[0], int(s.split(":")[1])) for s in sys.argv[4].split(",")]
+extra = dict(kv.split("=") for kv in sys.argv[5].split(",")) if len(sys.argv) > 5 and sys.argv[5] else {}
+for math in maths:
     for tk, tb in shapes:
-        tag = f"{math}/{tk}/t{tb}"
-        kw = dict(math=math, tile_kernel=tk, tile_bits=tb)
+        tag = f"{math}/{tk}/t{tb}" + "".join(f"/{k}={v}" for k, v in extra.items())
+        kw = dict(math=math, tile_kernel=tk, tile_bits=tb, **extra)
         if "qft" in what:
             run(n, [("qft",)], f"qft {tag}", **kw)
         if "random" in what:

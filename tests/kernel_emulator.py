@@ -120,11 +120,13 @@ def run_sharded(plans, n_qubits, world, fast, shards=None):
     return shards
 
 
-def run_pass(p, state, n_qubits, fast):
+def run_pass(p, state, n_qubits, fast, tables=None):
     """One fused pass over a shard of 2^n_qubits amplitudes: returns (store addresses, values)."""
     global _INV
     if _INV is None:
         _INV = _label_tables()
+    if tables is None and p.n_thread_tables:
+        tables = p.thread_tables.reshape(p.n_thread_tables, -1)   # plan_emulator.read_plan attaches them
     if True:
         T, R = p.tile_bits, p.reg_bits
         CT, NREG, n_tiles = 1 << (T - R), 1 << R, 1 << (n_qubits - T)
@@ -204,6 +206,22 @@ def run_pass(p, state, n_qubits, fast):
                     tabs.append(t)
                 return tabs
 
+            def ufan_factor(h):
+                """the kernel prologue's work for the uniform fan at record h: one factor per CTA from the tile's origin"""
+                g = p.gate[h]
+                K = g.tsel
+                if g.pad[0]:
+                    mask = (tile_full >> np.uint64(g.cpos)) & np.uint64((1 << K) - 1)
+                else:
+                    mask = np.zeros(n_tiles, dtype=np.uint64)
+                    for k in range(K):
+                        mask |= ((tile_full >> np.uint64(p.gate[h + 1 + k].cpos)) & np.uint64(1)) << np.uint64(k)
+                factor = np.ones(n_tiles, dtype=np.complex128)
+                for i, tab in enumerate(fan_tables(h, K)):
+                    nib = ((mask >> np.uint64(4 * i)) & np.uint64(15)).astype(np.int64)
+                    factor *= np.where(nib > 0, tab[nib], 1.0)
+                return factor
+
             gi = seg.gate_begin
             pending = np.ones((n_tiles, CT), dtype=np.complex128)          # math=fast: (fr, fi)
             while gi < seg.gate_end:
@@ -246,6 +264,19 @@ def run_pass(p, state, n_qubits, fast):
                             pending[active & tb] *= m[3]
                         else:
                             apply_factor(active & tb, reg_sel, m[3])
+                elif 235 <= base < 240:                                   # thread-table fan (math=fast)
+                    assert fast and tables is not None, "thread-table fans exist under math=fast only"
+                    t = base - 236
+                    h = gi - 1
+                    factor = np.broadcast_to(tables[g.tsel][None, :], (n_tiles, CT)).copy()
+                    if g.csel != 0xFF:
+                        factor *= ufan_factor(p.ufan_header[g.csel])[:, None]
+                    if t >= 0:
+                        apply_factor(np.ones((n_tiles, CT), dtype=bool), ((rbit >> t) & 1) == 1, factor)
+                    else:
+                        tb = xbit(g.tpos)
+                        pending[tb] *= factor[tb]
+                    gi += g.pad[1]
                 elif base < 240:                                          # diagonal, target = register bit t
                     k = (base - 175) // 3
                     halves = (base - 175) % 3 + 1
@@ -285,18 +316,7 @@ def run_pass(p, state, n_qubits, fast):
                     K, slot = g.tsel, g.csel
                     h = gi - 1
                     assert p.ufan_header[slot] == h and slot < p.n_ufans
-                    # prologue: one factor per CTA from the tile's origin
-                    if g.pad[0]:
-                        mask = (tile_full >> np.uint64(g.cpos)) & np.uint64((1 << K) - 1)
-                    else:
-                        mask = np.zeros(n_tiles, dtype=np.uint64)
-                        for k in range(K):
-                            mask |= ((tile_full >> np.uint64(p.gate[h + 1 + k].cpos)) & np.uint64(1)) << np.uint64(k)
-                    factor = np.ones(n_tiles, dtype=np.complex128)
-                    for i, tab in enumerate(fan_tables(h, K)):
-                        nib = ((mask >> np.uint64(4 * i)) & np.uint64(15)).astype(np.int64)
-                        factor *= np.where(nib > 0, tab[nib], 1.0)
-                    f2 = np.broadcast_to(factor[:, None], (n_tiles, CT))
+                    f2 = np.broadcast_to(ufan_factor(h)[:, None], (n_tiles, CT))
                     if t >= 0:
                         apply_factor(np.ones((n_tiles, CT), dtype=bool), ((rbit >> t) & 1) == 1, f2)
                     else:

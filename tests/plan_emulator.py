@@ -18,7 +18,7 @@ import numpy as np
 
 TILE_BITS, MAX_REG_BITS, MAX_SEGMENTS, MAX_GATES, MAX_FANS = 12, 4, 12, 240, 48
 GK_GENERIC, GK_REAL, GK_HSYM, GK_SWAP, GK_DIAG, GK_NOP = range(6)
-GF_ROW0_ONLY, GF_FAN_HEADER = 1, 0x80
+GF_ROW0_ONLY, GF_TFAN_HEADER, GF_FAN_HEADER = 1, 0x40, 0x80
 
 
 class DGate(ctypes.Structure):
@@ -48,7 +48,7 @@ class PassParams(ctypes.Structure):
                 ("tile_run", DTileRun * 12), ("goff", (ctypes.c_uint64 * MAX_REG_BITS) * 2),
                 ("seg", DSegment * MAX_SEGMENTS), ("gate", DGate * (MAX_GATES + MAX_FANS)),
                 ("ufan_header", ctypes.c_uint16 * MAX_FANS), ("n_ufans", ctypes.c_int32),
-                ("pad_", ctypes.c_int32)]
+                ("n_thread_tables", ctypes.c_int32)]
 
 
 def read_plan(circuit):
@@ -60,8 +60,60 @@ def read_plan(circuit):
     for k in range(n):
         p = PassParams()
         C.qcs_cuda_last_plan_raw(circuit.e, k, ctypes.byref(p), ctypes.sizeof(p))
+        p.thread_tables = read_tables(circuit, k)   # rides along as a plain attribute
+        check_thread_tables(p, p.thread_tables)
         out.append(p)
     return out
+
+
+def read_tables(circuit, pass_index):
+    """The thread-table fans that travel next to a pass (math=fast): array [table, thread id] of complex."""
+    C = circuit.C
+    n = C.qcs_cuda_last_plan_tables(circuit.e, pass_index, None, 0)
+    if n == 0:
+        return np.zeros((0, 0), dtype=np.complex128)
+    buf = np.empty(n, dtype=np.float64)
+    assert C.qcs_cuda_last_plan_tables(circuit.e, pass_index, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n) == n
+    return buf.view(np.complex128)
+
+
+def check_thread_tables(p, tables):
+    """Every thread-table fan of pass `p` against its own entry records: table[tid] must be the product of
+    the phases of the entries whose control the thread with id `tid` has set, `tid` mapped to tile-index
+    bits through the segment's role table exactly as the kernel maps it."""
+    T, R = p.tile_bits, p.reg_bits
+    CT = 1 << (T - R)
+    assert tables.size == p.n_thread_tables * CT
+    tables = tables.reshape(p.n_thread_tables, CT) if p.n_thread_tables else tables
+    tile_pos = [p.tile_pos[b] for b in range(T)]
+    seen = 0
+    for s in range(p.n_segments):
+        seg = p.seg[s]
+        for gi in range(seg.gate_begin, seg.gate_end):
+            g = p.gate[gi]
+            if not (g.flags & GF_TFAN_HEADER):
+                continue
+            assert g.tsel == seen, "tables are numbered in record order"
+            seen += 1
+            n_own = g.pad[2]
+            want = np.ones(CT, dtype=np.complex128)
+            for tid in range(CT):
+                tb = 0
+                for role in range(T - R):
+                    if (tid >> role) & 1:
+                        tb |= 1 << seg.role_tilebit[role]
+                for e in range(n_own):
+                    rec = p.gate[gi + 1 + e]
+                    assert rec.tpos == g.tpos and rec.cpos in tile_pos and rec.kind == GK_DIAG
+                    if (tb >> tile_pos.index(rec.cpos)) & 1:
+                        want[tid] *= complex(rec.m[6], rec.m[7])
+            assert np.abs(tables[g.tsel] - want).max() <= 1e-14, "thread table disagrees with its entries"
+            if g.csel != 0xFF:
+                h = gi + 1 + n_own
+                assert p.ufan_header[g.csel] == h and (p.gate[h].flags & GF_FAN_HEADER) and g.pad[1] == n_own + 1 + p.gate[h].tsel
+            else:
+                assert g.pad[1] == n_own
+    assert seen == p.n_thread_tables
 
 
 def _bit(idx, pos):
@@ -132,6 +184,13 @@ def run_plan(passes, n_qubits, fast, state=None):
             gi = seg.gate_begin
             while gi < seg.gate_end:
                 g = p.gate[gi]
+                if g.flags & GF_TFAN_HEADER:
+                    # thread-table fan (math=fast): the own entries behind the header are ordinary records --
+                    # applied one by one here; that their product is what the table holds is
+                    # check_thread_tables' business -- and a uniform fan may follow (handled below)
+                    assert gi + g.pad[1] <= seg.gate_end - 1, "thread-table fan crosses its segment"
+                    gi += 1
+                    continue
                 if g.flags & GF_FAN_HEADER:
                     assert gi + g.tsel <= seg.gate_end - 1, "fan crosses its segment"
                     if fast:
