@@ -607,6 +607,7 @@ def main() -> None:
         "gates_per_pass": gates / passes_per_step if passes_per_step else None,
         "remaps_per_step": st["remaps"] / args.steps,
         "fused_remaps_per_step": st["fused_remaps"] / args.steps,
+        "out_of_place_remaps_per_step": st["out_of_place_remaps"] / args.steps,
         "fused_remap_pass_ms": (st["fused_remap_pass_ms"] / st["fused_remaps"]) if st["fused_remaps"] else None,
         "roofline": {
             "bound": "hbm", "kernel": "fused_pass (tile kernel)",
@@ -765,7 +766,7 @@ def random_circuit_aux(Circuit, kw, world, barrier, dist, torch) -> dict:
     return {"workload": f"{n}-qubit random circuit (H/RZ/CNOT brickwork, depth 40, {len(script)} gates)",
             "gates_per_s": len(script) / dev_s, "seconds": dev_s, "passes": st["passes"],
             "amplitude_gate_updates_per_s_per_gpu": len(script) * 2.0 ** n / dev_s / world,
-            "remaps": st["remaps"], "fused_remaps": st["fused_remaps"],
+            "remaps": st["remaps"], "fused_remaps": st["fused_remaps"], "out_of_place_remaps": st["out_of_place_remaps"],
             "fused_remap_pass_ms_avg": (st["fused_remap_pass_ms"] / st["fused_remaps"]) if st["fused_remaps"] else None,
             "position_pairs_traded": st["remaps"], "carrying_passes_with_2_or_3_pairs": st["multi_remaps"],
             "nvlink_GBps_per_direction_in_fused_passes": (st["fused_remap_bytes"] / (st["fused_remap_pass_ms"] * 1e-3) / 1e9

@@ -155,6 +155,7 @@ typedef struct qcs_cuda_stats {
   long gates_cancelled;        /* dropped by the queue peephole (exact pairs) */
   long multi_remaps;           /* carrying passes that traded 2 or 3 position pairs at once (counted in fused_remaps) */
   double fused_remap_bytes;    /* bytes per direction this rank moved over NVLink inside carrying passes (part of exchange_bytes) */
+  long out_of_place_remaps;    /* carrying passes that wrote the ranks' second shard buffers (option remap_buffer): no per-tile handshake */
 } qcs_cuda_stats;
 
 int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out);

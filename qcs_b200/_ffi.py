@@ -32,6 +32,7 @@ class Stats(ctypes.Structure):
         ("fused_remaps", ctypes.c_long), ("fused_remap_pass_ms", _D),
         ("pass_flops_per_amp", _D), ("gates_cancelled", ctypes.c_long),
         ("multi_remaps", ctypes.c_long), ("fused_remap_bytes", _D),
+        ("out_of_place_remaps", ctypes.c_long),
     ]
 
     def as_dict(self) -> dict:

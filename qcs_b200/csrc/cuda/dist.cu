@@ -197,37 +197,55 @@ int dist_open_peers(Engine &e) {
     if (!e.swap_status_host) CK(cudaMallocHost(&e.swap_status_host, sizeof(int)));
     *e.swap_status_host = 0;
   }
-  struct Handles { cudaIpcMemHandle_t live, flags; } mine;
+  struct Handles { cudaIpcMemHandle_t live, alt, flags; int has_alt; } mine;
   std::memset(&mine, 0, sizeof(mine));
   CK(cudaIpcGetMemHandle(&mine.live, e.live));
   pool_pin(e.live);  // peers keep it mapped after this engine is gone
+  if (e.alt && e.tile_flags && cudaIpcGetMemHandle(&mine.alt, e.alt) == cudaSuccess) mine.has_alt = 1;
+  else cudaGetLastError();
   if (e.tile_flags) CK(cudaIpcGetMemHandle(&mine.flags, e.tile_flags));
   std::vector<Handles> all(d.world);
   int rc = dist_allgather_host(&mine, all.data(), sizeof(mine));
   if (rc) return rc;
+  // the second buffer is used by all ranks or by none
+  bool all_alt = true;
+  for (int r = 0; r < d.world; r++) all_alt = all_alt && all[r].has_alt;
+  auto drop_alt = [&]() {
+    pool_release(e.alt, e.local_size * sizeof(double2));
+    e.alt = nullptr;
+    e.peer_alt.clear();
+  };
+  if (!all_alt) drop_alt();
+  else pool_pin(e.alt);
   e.peer_live.assign(d.world, nullptr);
   e.peer_flags.assign(d.world, nullptr);
+  if (e.alt) e.peer_alt.assign(d.world, nullptr);
   for (int r = 0; r < d.world; r++) {
     if (r == d.rank) {
       e.peer_live[r] = e.live;
       e.peer_flags[r] = e.tile_flags;
+      if (e.alt) e.peer_alt[r] = e.alt;
       continue;
     }
     void *ptr = open_peer_cached(r, all[r].live);
     void *fptr = (ptr && e.tile_flags) ? open_peer_cached(r, all[r].flags) : nullptr;
-    if (!ptr || (e.tile_flags && !fptr)) {
+    void *aptr = (ptr && e.alt) ? open_peer_cached(r, all[r].alt) : nullptr;
+    if (!ptr || (e.tile_flags && !fptr) || (e.alt && !aptr)) {
       e.peer_live.clear();  // no peer access: the NCCL path stays in charge
       e.peer_flags.clear();
+      drop_alt();  // (every rank fails the same way: peer access is symmetric)
       return QCS_CUDA_OK;
     }
     e.peer_live[r] = (double2 *)ptr;
     e.peer_flags[r] = (uint32_t *)fptr;
+    if (e.alt) e.peer_alt[r] = (double2 *)aptr;
   }
   return QCS_CUDA_OK;
 }
 
 // qc_destroy: the mappings stay (cache above); the flag array goes back on the shelf.
 void dist_close_peers(Engine &e) {
+  e.peer_alt.clear();
   e.peer_live.clear();
   e.peer_flags.clear();
   for (FlagArray &f : g_flag_arrays)
@@ -297,7 +315,7 @@ bool dist_fused_swap_args(Engine &e, int k, const int *lpos, const int *gpos, Sw
       r = (r & ~(1 << gbit)) | (((b >> i) & 1) << gbit);
     }
     if (!e.peer_live[r] || !e.peer_flags[r]) return false;
-    sw.peer[b] = e.peer_live[r];
+    sw.peer[b] = e.alt ? e.peer_alt[r] : e.peer_live[r];
     sw.peer_flags[b] = e.peer_flags[r] + (size_t)sw.my_gbits * e.tile_flag_stride;
   }
   sw.my_flags = e.tile_flags;
@@ -306,6 +324,9 @@ bool dist_fused_swap_args(Engine &e, int k, const int *lpos, const int *gpos, Sw
   e.swap_epoch = sw.epoch;
   sw.abort_flag = e.swap_abort_flag;
   sw.spin_limit = swap_spin_limit();
+  sw.out_of_place = e.alt ? 1u : 0u;
+  sw.own_out = e.alt;
+  e.swap_out_of_place = e.alt != nullptr;
   return true;  // in_tile, n_out, out_pair, out_tile_bit, bulk, row_bits: the caller knows the pass's tile
 }
 
@@ -316,6 +337,15 @@ bool dist_fused_swap_args(Engine &e, int k, const int *lpos, const int *gpos, Sw
 // on any rank gave up waiting for its partner.
 int dist_after_fused_swap(Engine &e) {
   DistContext &d = dist();
+  if (e.swap_out_of_place) {
+    // the pass read `live` and wrote every rank's `alt`: the buffers trade roles -- on every rank, the pass
+    // is collective.  The all-reduce below is also what makes the old `live` safe to overwrite in the
+    // NEXT carrying pass: no rank gets past it before every rank's kernel has finished reading.
+    std::swap(e.live, e.alt);
+    std::swap(e.peer_live, e.peer_alt);
+    e.swap_out_of_place = false;
+    e.out_of_place_remaps++;
+  }
   int *flag = (int *)((char *)g_small_dev + kSmallBytes - 64);  // clear of dist_allgather_host's area
   CK(cudaMemcpyAsync(flag, e.swap_abort_flag, sizeof(int), cudaMemcpyDeviceToDevice, e.stream));
   NK(ncclAllReduce(flag, flag, 1, ncclInt, ncclSum, (ncclComm_t)d.comm, e.stream));

@@ -100,6 +100,11 @@ static int load_options(Options &o) {
   v = option_value("fan_tables");
   // "off" | "on" | the fewest in-tile controls a run needs to become a table (on = 2)
   o.fan_tables = (v == "off" || v == "0") ? 0 : (v.empty() || v == "on") ? 2 : std::max(2, std::atoi(v.c_str()));
+  v = option_value("remap_buffer");
+  if (v == "auto") o.remap_buffer = 0;
+  else if (v.empty() || v == "inplace") o.remap_buffer = 1;
+  else if (v == "double") o.remap_buffer = 2;
+  else return set_error(QCS_CUDA_ERR_INVALID, "remap_buffer must be auto|inplace|double, got '%s'", v.c_str());
   v = option_value("victim_policy");
   if (v == "lru") o.victim_policy = 0;
   else if (v.empty() || v == "mru") o.victim_policy = 1;
@@ -192,6 +197,19 @@ cudaError_t pool_alloc(void **out, size_t bytes) {
   }
   return e;
 }
+// a buffer of exactly this size if the pool holds one (no cudaMalloc)
+bool pool_take_cached(void **out, size_t bytes) {
+  std::lock_guard<std::mutex> lock(globals_mutex());
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (size_t i = 0; i < g_pool.size(); i++)
+    if (g_pool[i].bytes == bytes && g_pool[i].device == dev) {
+      *out = g_pool[i].ptr;
+      g_pool.erase(g_pool.begin() + (long)i);
+      return true;
+    }
+  return false;
+}
 void pool_free(void *ptr, size_t bytes) {
   if (!ptr) return;
   std::lock_guard<std::mutex> lock(globals_mutex());
@@ -221,6 +239,8 @@ void pool_free(void *ptr, size_t bytes) {
   }
 }
 }  // namespace
+
+void pool_release(void *ptr, size_t bytes) { pool_free(ptr, bytes); }
 
 void pool_pin(void *ptr) {
   std::lock_guard<std::mutex> lock(globals_mutex());
@@ -1136,7 +1156,28 @@ int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
   e->zero_ket_pending = true;
   if (!e->opt.lazy_init && (rc = materialize(*e))) return fail(rc);
   if ((rc = check_cuda(cudaStreamSynchronize(e->stream), "init sync"))) return fail(rc);
+  if (d.active && e->opt.exchange == 1 && e->opt.fuse_swaps && e->opt.remap_buffer != 1 &&
+      e->opt.sem == SEM_CORRECTED && e->nl >= QCS_MIN_TILE_BITS) {
+    // Second shard buffer for the passes that carry a remap (kernels.h SwapStore::out_of_place).  auto: a
+    // buffer the pool already holds, else a fresh one only while an eighth of the device stays free;
+    // dist_open_peers drops it again unless every rank got one.
+    const size_t bytes = e->local_size * sizeof(double2);
+    void *buf = nullptr;
+    if (!pool_take_cached(&buf, bytes)) {
+      size_t free_b = 0, total_b = 0;
+      bool fits = e->opt.remap_buffer == 2;
+      if (!fits && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) fits = free_b >= bytes + total_b / 8;
+      if (fits && pool_alloc(&buf, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        buf = nullptr;
+      }
+    }
+    e->alt = (double2 *)buf;
+  }
   if (d.active && e->opt.exchange == 1 && (rc = dist_open_peers(*e))) return fail(rc);
+  if (e->opt.remap_buffer == 2 && d.active && !e->alt)
+    return fail(set_error(QCS_CUDA_ERR_CUDA, "remap_buffer=double: no second shard buffer on every rank (memory, or "
+                                             "no peer access / exchange=nccl / semantics=reference)"));
   *out = e;
   return QCS_CUDA_OK;
 }
@@ -1157,6 +1198,7 @@ void qcs_cuda_state_destroy(qcs_cuda_engine *e) {
   for (auto ev : e->markers) if (ev) cudaEventDestroy(ev);
   pool_free(e->live, e->local_size * sizeof(double2));
   pool_free(e->scratch, e->local_size * sizeof(double2));
+  pool_free(e->alt, e->local_size * sizeof(double2));
   pool_free(e->staging, e->local_size * sizeof(double2));
   pool_free(e->ws_slab, e->ws_slab_bytes);
   cudaFree(e->u_dev);
@@ -1534,6 +1576,7 @@ int qcs_cuda_get_stats(qcs_cuda_engine *e, qcs_cuda_stats *out) {
   out->pass_flops_per_amp = e->pass_flops_per_amp;
   out->gates_cancelled = e->gates_cancelled;
   out->multi_remaps = e->multi_remaps;
+  out->out_of_place_remaps = e->out_of_place_remaps;
   out->fused_remap_bytes = e->fused_swap_bytes;
   return QCS_CUDA_OK;
 }
@@ -1546,6 +1589,7 @@ int qcs_cuda_reset_stats(qcs_cuda_engine *e) {
   e->fused_swaps = 0;
   e->fused_swap_bytes = 0;
   e->multi_remaps = 0;
+  e->out_of_place_remaps = 0;
   e->gates_cancelled = 0;
   e->fused_swap_pass_ms = 0;
   e->pass_flops_per_amp = 0;

@@ -42,6 +42,11 @@ struct Options {
   int remap_max = 3;       // position pairs one carrying pass may trade (1..3): an all-to-all among 2^k ranks
   bool fuse_argmax = true; // qc_find_most_likely_state folds its first reduction level into the pass it flushes
   bool lazy_init = true;   // qc_create writes nothing; see Engine::zero_ket_pending
+  int remap_buffer = 1;    // 1 inplace (default): carrying passes overwrite the ranks' shards behind a per-tile
+                           // handshake; 0 auto: into a second shard buffer when it fits (kernels.h
+                           // SwapStore::out_of_place: no flags, no waits), 2 double: required.  Measured equal
+                           // in speed on 2 and 8 GPUs (profiles/r2q_bench_8gpu.json vs r2p, r2r_carry_probe.log),
+                           // so the default does not spend the memory.
   bool swap_bulk = true;   // such a pass hands the amplitudes that leave to TMA bulk stores (row-sized NVLink
                            // writes out of shared memory) instead of 16-byte st.global from the compute threads
   int tile_kernel = 3;  // 0: ldg (256 thr x 16 amps, plain loads), 1: tma16 (TMA, 256 x 16), 2: tma (TMA, 512 x 8), 3: ldg8 (512 thr x 8 amps, plain loads; default)
@@ -69,6 +74,8 @@ struct Engine {
   double2 *scratch = nullptr;  // reference: state->scratch_vector (lazily allocated)
   double2 *staging = nullptr;  // half-shard exchange buffer (multi-GPU, NCCL path)
   std::vector<double2 *> peer_live;  // every rank's state buffer mapped through CUDA IPC (P2P path)
+  double2 *alt = nullptr;            // second shard buffer: carrying passes read `live`, write every rank's `alt`,
+  std::vector<double2 *> peer_alt;   // and the two trade places (multi-GPU P2P path, when memory allows)
   cudaStream_t stream = nullptr;
   uint32_t *tile_flags = nullptr;         // one word per tile: handshake of passes that swap on the way out
   std::vector<uint32_t *> peer_flags;     // every rank's tile_flags, peer-mapped
@@ -76,6 +83,7 @@ struct Engine {
   uint32_t tile_flag_stride = 0;          // words per sending rank in tile_flags
   uint32_t *swap_abort_flag = nullptr;    // device word behind tile_flags: a CTA gave up waiting for its partner
   int *swap_status_host = nullptr;        // pinned: all-reduced abort words of the last swap-carrying pass
+  bool swap_out_of_place = false;         // the carrying pass being launched writes `alt` (dist_fused_swap_args)
   bool swap_status_pending = false;       // a status copy is in flight on the stream
   bool poisoned = false;                  // a failed flush / swap left the amplitudes undefined: every later
                                           // call that needs them returns the error
@@ -114,6 +122,7 @@ struct Engine {
             segments = 0, remaps = 0;
   long long gates_cancelled = 0;  // dropped by the queue peephole
   long long multi_remaps = 0;  // carrying passes that traded more than one position pair
+  long long out_of_place_remaps = 0;  // carrying passes that wrote the second buffer (no handshake)
   long long fused_swaps = 0;   // remaps that rode on a pass instead of getting a kernel of their own
   double algorithmic_bytes = 0, pass_bytes = 0, pass_ms = 0, exchange_bytes = 0, exchange_ms = 0;
   double pass_flops_per_amp = 0;  // planner's FP64 operation count per amplitude, summed over executed passes
@@ -135,6 +144,7 @@ struct Engine {
 // a pooled buffer whose CUDA IPC handle other ranks may hold mapped: never cudaFree'd (it stays in the
 // pool, whatever the pool's size limits say) until pool_unpin_all
 void pool_pin(void *ptr);
+void pool_release(void *ptr, size_t bytes);  // = pool_free, for dist.cu
 void pool_unpin_all();
 int set_error(int code, const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);

@@ -41,6 +41,12 @@ struct SwapStore {
   uint32_t *abort_flag;              // my own device word: set when a CTA gave up waiting for a partner (the tile
                                      // is then NOT stored and the engine reports QCS_CUDA_ERR_CUDA); later CTAs bail out
   unsigned long long spin_limit;     // clock64 ticks a CTA waits for a partner's signal before giving up
+  uint32_t out_of_place;             // 1: peer[] are the ranks' SECOND shard buffers (Engine::alt) -- every tile of
+                                     // the pass, the ones that stay included, is stored there and the buffers
+                                     // trade roles behind the pass.  Nothing a partner still has to read is
+                                     // overwritten, so there are no flags, no signal and no wait: the ranks run
+                                     // the pass at their own pace.  0: in place, with the per-tile handshake.
+  double2 *own_out;                  // out_of_place: peer[my_gbits], my own second buffer (no indexed parameter read)
 };
 // fast (ldg8 only): the fused-multiply-add interpreter; `params` must come from a planner run with
 // PlannerConfig::fast_math (fan entries carry product tables instead of single phases).

@@ -94,17 +94,23 @@ def main():
         po.replay(orc, script)
         # swaps on the stores of a pass through TMA bulk stores (default) / 16-byte stores, or stand-alone
         # and with up to 3 positions traded on one pass (an all-to-all among 2^k ranks) or one at a time
-        for fuse, store in (("on", "bulk"), ("on", "thread"), ("off", None)):
+        # ... into the ranks' second shard buffers (remap_buffer=double: no handshake, what `auto` picks
+        # while memory allows) or in place behind the per-tile handshake (remap_buffer=inplace)
+        for fuse, store, rbuf in (("on", "bulk", "double"), ("on", "thread", "double"), ("on", "bulk", "inplace"),
+                                  ("on", "thread", "inplace"), ("off", None, None)):
             for tile_bits in ((10, 11, 12) if fuse == "on" else (11,)):
                 for remap_max in ((3, 1) if fuse == "on" and world >= 4 else (3,)):
                     c = Circuit(n, semantics="corrected", fuse_swaps=fuse, swap_store=store, tile_bits=tile_bits,
-                                remap_max=remap_max)
+                                remap_max=remap_max, remap_buffer=rbuf)
                     po.replay(c, script); c.flush(); st = c.stats()
                     first, count = c._shard()
                     got = c.state(); want = orc.state()[first:first + count]
-                    tag = f"{name}/fuse_swaps={fuse}/{store}/t{tile_bits}/remap_max={remap_max}"
+                    tag = f"{name}/fuse_swaps={fuse}/{store}/{rbuf}/t{tile_bits}/remap_max={remap_max}"
                     check(np.all(got == want), f"{tag}: {int(np.sum(got != want))} shard amplitudes differ")
                     check((st["fused_remaps"] > 0) == (fuse == "on"), f"{tag}: fused_remaps={st['fused_remaps']}")
+                    if fuse == "on":
+                        check(st["out_of_place_remaps"] == (st["fused_remaps"] if rbuf == "double" else 0),
+                              f"{tag}: out_of_place_remaps={st['out_of_place_remaps']} of {st['fused_remaps']}")
                     if remap_max == 1:
                         check(st["multi_remaps"] == 0, f"{tag}: multi_remaps={st['multi_remaps']}")
                     multi_seen[0] += st["multi_remaps"]
