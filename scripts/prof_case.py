@@ -1,4 +1,4 @@
-"""Runs one small workload for ncu captures: python scripts/prof_case.py <case> <n> [tile_kernel]."""
+"""Runs one small workload for ncu captures: python scripts/prof_case.py <case> <n> [tile_kernel] [math]."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qcs_b200 import Circuit
@@ -11,7 +11,8 @@ scripts = {
     "qft": [("qft",)],
     "random": po.random_circuit_script(n, 2),
 }
-c = Circuit(n, semantics="corrected", tile_kernel=tk)
+math = sys.argv[4] if len(sys.argv) > 4 else "exact"
+c = Circuit(n, semantics="corrected", tile_kernel=tk, math=math)
 for _ in range(2):
     po.replay(c, scripts[case]); c.flush()
 print(c.stats())
