@@ -45,9 +45,9 @@ class Circuit:
                  swap_store: str | None = None, lazy_init: str | None = None,
                  fuse_argmax: str | None = None, remap_max: int | None = None,
                  victim_policy: str | None = None, fan_tables: str | None = None,
-                 remap_buffer: str | None = None):
+                 remap_buffer: str | None = None, tile_search: str | None = None):
         self.H, self.C = _ffi.load()
-        opts = {"semantics": semantics, "fusion": fusion, "tile_kernel": tile_kernel, "exchange": exchange, "fuse_swaps": fuse_swaps, "peephole": peephole, "math": math, "reorder": reorder, "swap_store": swap_store, "lazy_init": lazy_init, "fuse_argmax": fuse_argmax, "victim_policy": victim_policy, "fan_tables": fan_tables, "remap_buffer": remap_buffer,
+        opts = {"semantics": semantics, "fusion": fusion, "tile_kernel": tile_kernel, "exchange": exchange, "fuse_swaps": fuse_swaps, "peephole": peephole, "math": math, "reorder": reorder, "swap_store": swap_store, "lazy_init": lazy_init, "fuse_argmax": fuse_argmax, "victim_policy": victim_policy, "fan_tables": fan_tables, "remap_buffer": remap_buffer, "tile_search": tile_search,
                 "remap_max": None if remap_max is None else str(int(remap_max)),
                 "reorder_segments": None if reorder_segments is None else str(int(reorder_segments)), "fixed_low": None if fixed_low is None else str(int(fixed_low)),
                 "tile_bits": None if tile_bits is None else str(int(tile_bits)),

@@ -97,6 +97,8 @@ static int load_options(Options &o) {
   else return set_error(QCS_CUDA_ERR_INVALID, "exchange must be p2p|nccl, got '%s'", v.c_str());
   v = option_value("fuse_swaps");
   o.fuse_swaps = !(v == "off" || v == "0");
+  v = option_value("tile_search");
+  o.tile_search = !(v == "off" || v == "0");
   v = option_value("fan_tables");
   // "off" | "on" | the fewest in-tile controls a run needs to become a table (on = 2)
   o.fan_tables = (v == "off" || v == "0") ? 0 : (v.empty() || v == "on") ? 2 : std::max(2, std::atoi(v.c_str()));
@@ -361,7 +363,10 @@ static int min_tile_bits(const Engine &e) {
   return QCS_TILE_BITS;  // the TMA-staged kernels exist for 12-bit tiles only
 }
 
-static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysGate> &gates) {
+// whole_batch: every planned pass is launched before anything else happens to the state (run_local), so
+// the passes may take the batch's gates out of order where that is exact (PlannerConfig::reorder_exact);
+// the sharded in-order path launches a prefix of the plan and counts gates by position: in order only.
+static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysGate> &gates, bool whole_batch = false) {
   PlannerConfig cfg;
   cfg.n_local = e.nl;
   cfg.rank_bits = e.n - e.nl;
@@ -375,11 +380,25 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
   cfg.fast_math = e.opt.fast_math;
   // (sharded engines: run_range_reordered keeps track of which gates a pass took)
   cfg.reorder = e.opt.fast_math && e.opt.reorder;
+  cfg.reorder_exact = whole_batch && !e.opt.fast_math && e.opt.reorder && e.opt.sem == SEM_CORRECTED;
   cfg.reorder_segments = e.opt.reorder_segments;
   cfg.thread_tables = e.opt.fan_tables;
   cfg.tile_bits_min = min_tile_bits(e);
   cfg.tile_bits_max = std::max(cfg.tile_bits_min, std::min(e.opt.tile_bits, e.nl));
-  return plan_passes(gates, cfg);
+  std::vector<PassPlan> best = plan_passes(gates, cfg);
+  // Larger tiles exist to save passes.  When a smaller cap needs no more of them, its plan wins: the
+  // same gates spread evenly over more CTAs per SM (30-qubit QFT, 5 passes either way: targets
+  // 10+5+5+5+5 on 10-bit tiles against 11+6+6+6+1 with 11 allowed -- 62.3 vs 63.6 ms bit-exact, 34.4 vs
+  // 36.4 ms fast; the random circuits keep their 11-bit plans, which are passes shorter).  Planning is
+  // repeated once per smaller cap, so only for queues where that is cheap.
+  if (e.opt.tile_search && gates.size() <= 1024)
+    for (int cap = cfg.tile_bits_max - 1; cap >= cfg.tile_bits_min; cap--) {
+      PlannerConfig smaller = cfg;
+      smaller.tile_bits_max = cap;
+      std::vector<PassPlan> alt = plan_passes(gates, smaller);
+      if (alt.size() <= best.size()) best.swap(alt);
+    }
+  return best;
 }
 
 // Launches planned passes [first, last); `swap` (may be null) rides on the stores of the last one.
@@ -490,7 +509,7 @@ static int run_local(Engine &e, const std::vector<PhysGate> &gates) {
   if (e.opt.dryrun) trace_gates(e, gates);
   const bool fused = e.opt.fusion && e.nl >= min_tile_bits(e);
   if (fused) {
-    std::vector<PassPlan> plan = plan_batch(e, gates);
+    std::vector<PassPlan> plan = plan_batch(e, gates, true);
     RC(launch_passes(e, plan, 0, plan.size(), nullptr));
   } else {
     RC(materialize(e));
@@ -761,7 +780,19 @@ static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, si
       i = x;
       continue;
     }
-    if (e.opt.dryrun) trace_gates(e, std::vector<PhysGate>(batch.begin(), batch.begin() + (long)(pass_end - i)));
+    const std::vector<PhysGate> prefix(batch.begin(), batch.begin() + (long)(pass_end - i));
+    if (e.opt.dryrun) trace_gates(e, prefix);
+    {
+      // The gates that run before the remap are now fixed (a prefix of the queue): plan just those again,
+      // out of order where that is exact (PlannerConfig::reorder_exact), and let the remap ride on the
+      // last pass -- legal wherever the in-order plan's carrying pass was, since every gate of the prefix
+      // has been applied by then.  Kept when it needs fewer passes.
+      std::vector<PassPlan> again = plan_batch(e, prefix, true);
+      if (!again.empty() && again.size() < chosen + 1) {
+        plan.swap(again);
+        chosen = plan.size() - 1;
+      }
+    }
     RC(launch_passes(e, plan, 0, chosen + 1, &sw, k_pairs, lpos_k, gpos_k));
     for (int j = 0; j < k_pairs; j++) note_swap(e, lpos_k[j], gpos_k[j]);
     // bytes that crossed NVLink per direction: (1 - 2^-k) of the shard, not k halves

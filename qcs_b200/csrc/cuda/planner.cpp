@@ -657,11 +657,15 @@ struct Sweep {
   int pairing = 0;          // pairing gates among them
 };
 
+// exact: only gates that move amplitudes without arithmetic (GK_PAIR_SWAP) may pass a pending gate or be
+// passed by one -- a gate that rounds never overtakes another gate that rounds, not even on other qubits
+// (A then B and B then A round different intermediates).
 Sweep sweep_executable(const std::vector<PhysGate> &g, const std::vector<char> &done, size_t first,
-                       uint64_t rmask, int n_positions, size_t window, bool collect) {
+                       uint64_t rmask, int n_positions, size_t window, bool collect, bool exact = false) {
   Sweep s;
   uint8_t state[64] = {0};
   int n_full = 0;
+  bool rounding_gate_pending = false;
   size_t seen = 0, last_pick = 0;
   const size_t patience = 16 * (size_t)n_positions + 16;  // gates scanned without a pick before giving up
   for (size_t i = first; i < g.size() && seen < window && n_full < n_positions; i++) {
@@ -676,6 +680,9 @@ Sweep sweep_executable(const std::vector<PhysGate> &g, const std::vector<char> &
     const bool pairing = is_pairing(x.c.kind);
     bool ok = pairing ? (((rmask >> x.tpos) & 1ull) && state[x.tpos] == 0) : state[x.tpos] <= 1;
     if (ok && x.cpos >= 0 && state[x.cpos] > 1) ok = false;
+    const bool moves_only = x.c.kind == GK_PAIR_SWAP;
+    if (ok && exact && !moves_only && rounding_gate_pending) ok = false;
+    if (!ok && !moves_only) rounding_gate_pending = true;
     if (ok) {
       if (collect) s.picked.push_back((int)i);
       s.pairing += pairing ? 1 : 0;
@@ -694,9 +701,10 @@ Sweep sweep_executable(const std::vector<PhysGate> &g, const std::vector<char> &
 
 std::vector<PassPlan> plan_passes_reordered(const std::vector<PhysGate> &gates, const PlannerConfig &cfg_in) {
   PlannerConfig cfg = cfg_in;
+  const bool exact = !cfg.fast_math;
   // the tile is chosen here, not by the builder's growth rule (stopping heavy passes at 10 bits as the
   // in-order planner does was measured: QFT unchanged, 31-qubit random circuit 3 % slower)
-  cfg.compute_bound_flops = 1e30;
+  if (!exact) cfg.compute_bound_flops = 1e30;
   const int n_positions = cfg.n_local + cfg.rank_bits;
   const size_t window = 4096;
   std::vector<PassPlan> out;
@@ -725,7 +733,7 @@ std::vector<PassPlan> plan_passes_reordered(const std::vector<PhysGate> &gates, 
           if ((rmask >> q) & 1ull) continue;
           const bool in_tile = (tile_mask >> q) & 1ull;
           if (!in_tile && tile_size + __builtin_popcountll(rmask & ~tile_mask) >= cfg.tile_bits_max) continue;
-          const int gain = sweep_executable(gates, done, first, rmask | (1ull << q), n_positions, window, false).pairing -
+          const int gain = sweep_executable(gates, done, first, rmask | (1ull << q), n_positions, window, false, exact).pairing -
                            base_pairing;
           // ties: a position the tile already holds (keeps the tile small / leaves room), then the lowest
           if (gain > best_gain || (gain == best_gain && gain > 0 && in_tile && !best_in_tile)) {
@@ -738,7 +746,7 @@ std::vector<PassPlan> plan_passes_reordered(const std::vector<PhysGate> &gates, 
         rmask |= 1ull << best;
         base_pairing += best_gain;
       }
-      Sweep sw = sweep_executable(gates, done, first, rmask, n_positions, window, true);
+      Sweep sw = sweep_executable(gates, done, first, rmask, n_positions, window, true, exact);
       if (sw.picked.empty()) break;
       size_t added = 0;
       for (int i : sw.picked) {
@@ -795,6 +803,17 @@ std::vector<PassPlan> plan_passes(const std::vector<PhysGate> &gates_in, const P
   if (cfg.fast_math)
     for (PhysGate &g : gates) g.c.flops_per_amp = fast_flops(g);
   if (cfg.fast_math && cfg.reorder) return plan_passes_reordered(gates, cfg);
+  if (!cfg.fast_math && cfg.reorder_exact && cfg.sem == SEM_CORRECTED) {
+    // worth trying only when something in the queue may move at all; kept only when it saves passes
+    bool any = false;
+    for (const PhysGate &g : gates) any = any || g.c.kind == GK_PAIR_SWAP;
+    if (any) {
+      PlannerConfig in_order = cfg;
+      in_order.reorder_exact = false;
+      std::vector<PassPlan> a = plan_passes(gates_in, in_order), b2 = plan_passes_reordered(gates, cfg);
+      return b2.size() < a.size() ? b2 : a;
+    }
+  }
   PassBuilder *b = new PassBuilder(cfg);
   for (size_t i = 0; i < gates.size(); i++) {
     const PhysGate &g = gates[i];

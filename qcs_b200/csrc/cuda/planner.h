@@ -68,6 +68,10 @@ struct PlannerConfig {
   bool reorder = false;     // math=fast only: gates that commute (every shared qubit is a control or a diagonal
                             // target of both) may trade places, so a pass is a SUBSEQUENCE of the queue
                             // chosen to keep a tile busy over several circuit layers (plan_passes_reordered)
+  bool reorder_exact = false;  // bit-exact mode, corrected semantics: the same scheduler under the one commutation
+                            // that is exact in floating point -- a gate that only MOVES amplitudes (X, CNOT:
+                            // GK_PAIR_SWAP) trades places with any gate it commutes with; two gates that both
+                            // round never do, whatever qubits they act on.  Used when it saves passes.
   int reorder_segments = 8; // segments a reordered pass may spend before the next pass starts
   int thread_tables = 2;  // math=fast: runs of controlled phases with in-tile controls become one table
                             // lookup per thread (common.h QCS_OP_TFAN_BASE) instead of a walk over product tables

@@ -39,12 +39,12 @@ what = sys.argv[2].split(",") if len(sys.argv) > 2 else ["qft", "random", "rz", 
 maths = sys.argv[3].split(",") if len(sys.argv) > 3 and sys.argv[3] else ["exact", "fast"]
 shapes = [("ldg8", 10), ("ldg8", 11), ("ldg", 10), ("ldg", 11), ("ldg", 12)]
 if len(sys.argv) > 4 and sys.argv[4]:
-    shapes = [(s.split(":")[0], int(s.split(":")[1])) for s in sys.argv[4].split(",")]
+    shapes = [(s.split(":")[0], int(s.split(":")[1]) if ":" in s else None) for s in sys.argv[4].split(",")]
 extra = dict(kv.split("=") for kv in sys.argv[5].split(",")) if len(sys.argv) > 5 and sys.argv[5] else {}
 for math in maths:
     for tk, tb in shapes:
         tag = f"{math}/{tk}/t{tb}" + "".join(f"/{k}={v}" for k, v in extra.items())
-        kw = dict(math=math, tile_kernel=tk, tile_bits=tb, **extra)
+        kw = dict(math=math, tile_kernel=tk, tile_bits=tb, **extra)   # tile_bits None = the engine's default
         if "qft" in what:
             run(n, [("qft",)], f"qft {tag}", **kw)
         if "random" in what:

@@ -75,17 +75,53 @@ def test_plan_invariants_random_circuit(n, tile_kernel, reg_bits, tile_bits):
     assert len(passes) * 3 < len(script)
 
 
-def test_gate_order_is_preserved():
-    n = 16
-    script = po.random_circuit_script(n, 3, seed=5)
-    text, _ = _plan(n, script, semantics="corrected")
+def _order_case(n=16, depth=3, seed=5, **kw):
+    script = po.random_circuit_script(n, depth, seed=seed)
+    text, _ = _plan(n, script, semantics="corrected", **kw)
     flat = [g for p in _parse(text) for s in p["segs"] for g in s["gates"]]
     want = []
     for op in script:
         if op[0] == "h": want.append(("hsym", -1, op[1]))
         elif op[0] == "rz": want.append(("diag", -1, op[1]))
         elif op[0] == "cnot": want.append(("swap", op[1], op[2]))
+    return flat, want
+
+
+def test_gate_order_is_preserved():
+    flat, want = _order_case(reorder="off")
     assert flat == want
+
+
+def test_exact_mode_only_moves_gates_that_move_amplitudes():
+    """Default bit-exact schedule (PlannerConfig::reorder_exact): gates that round keep their relative
+    order, whatever qubits they act on; a CNOT (moves only) may trade places with a gate it commutes
+    with -- never with one that pairs on one of its qubits or is diagonal on its target."""
+    flat, want = _order_case(depth=6)
+    assert sorted(flat) == sorted(want)
+    assert flat != want, "the case is meant to exercise a reordered plan"
+    assert [g for g in flat if g[0] != "swap"] == [g for g in want if g[0] != "swap"]
+    # brickwork: every gate is unique per (layer, qubits) but tuples repeat across layers -- match the
+    # k-th occurrence of a tuple in the plan with its k-th occurrence in the script (a gate never
+    # overtakes an identical one: same qubits, at least one pairing use)
+    seen, where = {}, {}
+    for i, g in enumerate(flat):
+        k = seen.get(g, 0); seen[g] = k + 1
+        where[(g, k)] = i
+    seen, pos = {}, []
+    for g in want:
+        k = seen.get(g, 0); seen[g] = k + 1
+        pos.append(where[(g, k)])
+    pairing = {"hsym", "swap", "generic", "real"}
+    for a in range(len(want)):
+        for b in range(a + 1, len(want)):
+            ka, ca, ta = want[a]; kb, cb, tb = want[b]
+            conflict = False
+            for q in {ca, ta} & {cb, tb} - {-1}:
+                a_pairs = ka in pairing and q == ta
+                b_pairs = kb in pairing and q == tb
+                conflict = conflict or a_pairs or b_pairs
+            if conflict:
+                assert pos[a] < pos[b], (want[a], want[b])
 
 
 def test_qft30_plan_is_compact():
@@ -254,6 +290,61 @@ def test_reordered_plans_on_random_gate_soup(seed):
     c.close()
     assert sum(p["api"] for p in _parse(text)) == len(script), "every queued gate belongs to exactly one pass"
     _close(pe.run_plan(passes, n, fast=True), want)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_exact_reordered_plans_are_bit_exact(seed):
+    """The bit-exact mode's schedule (PlannerConfig::reorder_exact) may move X / CNOT past gates they commute
+    with and nothing else.  The order the plan executes the gates in, replayed gate by gate on the CPU
+    oracle, must give the SAME BITS as the order the circuit was written in -- and through the plan
+    emulator the oracle's state."""
+    from qcs_b200 import Circuit
+    from tests import plan_emulator as pe
+    rng = np.random.default_rng(300 + seed)
+    n = int(rng.integers(11, 15))
+    if seed % 3 == 0:
+        n = 16 + seed // 3          # wider than a tile: the in-order plan needs more passes
+        script = po.random_circuit_script(n, int(rng.integers(4, 12)), seed=seed)
+    else:
+        script = []
+        for _ in range(int(rng.integers(60, 300))):
+            q = int(rng.integers(0, n))
+            c = int(rng.integers(0, n - 1)); c = c if c < q else c + 1
+            a = float(rng.uniform(-3, 3))
+            script.append([("h", q), ("x", q), ("cnot", c, q), ("cnot", c, q), ("rz", q, a), ("ry", q, a),
+                           ("cphase", c, q, a)][int(rng.integers(0, 7))])
+    kind_of = {"h": "hsym", "x": "swap", "cnot": "swap", "rz": "diag", "ry": "real", "cphase": "diag"}
+    key = lambda op: (kind_of[op[0]], op[1] if op[0] in ("cnot", "cphase") else -1, op[2] if op[0] in ("cnot", "cphase") else op[1])
+    tile_bits = [10, 11, 12][seed % 3]   # (brickwork cases: 10)
+    c = Circuit(n, dryrun=True, semantics="corrected", tile_bits=tile_bits, peephole="off")
+    po.replay(c, script)
+    c.flush()
+    flat = [g for p in _parse(c.describe_plan()) for s in p["segs"] for g in s["gates"]]
+    passes = pe.read_plan(c)
+    c.close()
+    assert sorted(flat) == sorted(key(op) for op in script)
+    # k-th occurrence of a (kind, control, target) in the plan = its k-th occurrence in the script
+    queues = {}
+    for op in script:
+        queues.setdefault(key(op), []).append(op)
+    taken = {}
+    executed = []
+    for g in flat:
+        k = taken.get(g, 0); taken[g] = k + 1
+        executed.append(queues[g][k])
+    start = np.random.default_rng(seed).normal(size=2 << n).view(np.complex128)[: 1 << n].copy()
+    start /= np.linalg.norm(start)
+    states = []
+    for order in (script, executed):
+        orc = po.Oracle(n, "corrected")
+        orc.load_state(start)
+        po.replay(orc, order)
+        states.append(orc.state())
+        orc.close()
+    assert np.array_equal(states[0].view(np.uint64), states[1].view(np.uint64)), "the executed order rounds differently"
+    _close(pe.run_plan(passes, n, fast=False, state=start.copy()), states[0])
+    if seed % 3 == 0:
+        assert executed != list(script), "brickwork circuits are where the reordering pays: it must happen here"
 
 
 # ---- the kernel's own view of a plan: role tables, addresses, case labels (tests/kernel_emulator.py) ---
