@@ -5,10 +5,13 @@
 // reference itself applies every gate eagerly with one full sweep per gate
 // (reference src/qcs.c:159-164 -> src/q_gates.c:131-148).  The planner takes
 // the deferred queue and cuts it, IN ORDER, into passes and segments
-// (common.h).  Gates are never reordered or algebraically merged, so the
-// arithmetic each amplitude sees is the reference's, operation by operation.
-// (The opt-in math=fast mode gives that up: FMA arithmetic, fan tables and --
-// PlannerConfig::reorder -- commuting gates scheduled out of order.)
+// (common.h).  Gates are never algebraically merged and two gates that both
+// round never trade places, so the arithmetic each amplitude sees is the
+// reference's, operation by operation; gates that only MOVE amplitudes (X,
+// CNOT) may be scheduled past gates they commute with, which changes no bit
+// (PlannerConfig::reorder_exact).  (The opt-in math=fast mode gives the rest
+// up: FMA arithmetic, fan tables and -- PlannerConfig::reorder -- every
+// commuting pair scheduled out of order.)
 #pragma once
 #include <string>
 #include <vector>
