@@ -1157,8 +1157,8 @@ int qcs_cuda_state_create(qcs_cuda_engine **out, int n_qubits) {
                          up(RES_COUNT * sizeof(double)), up(4 * sizeof(long long)),
                          up(n_chunks * sizeof(double)), up((n_chunks + 1) * sizeof(double)),
                          up(n_chunks * sizeof(double)), up(n_chunks), up((n_chunks + 1) * sizeof(double)),
-                         up((n_chunks / 1024 + 2) * sizeof(double)), up((n_chunks / 1024 + 2) * sizeof(double)),
-                         up(n_chunks / 1024 + 2), up(n_chunks * sizeof(double)), up(n_chunks * sizeof(double)),
+                         up((n_chunks / QCS_RESOLVE_GROUP + 2) * sizeof(double)),
+                         up((n_chunks / QCS_RESOLVE_GROUP + 2) * sizeof(double)), up(n_chunks / QCS_RESOLVE_GROUP + 2), up(n_chunks * sizeof(double)), up(n_chunks * sizeof(double)),
                          up(n_chunks * sizeof(double))};
     size_t total = 0;
     for (size_t b : sz) total += b;
@@ -1337,8 +1337,10 @@ int qcs_cuda_diffusion(qcs_cuda_engine *e) {
     e->kernel_launches++;
     for (int comp = 0; comp < 2; comp++) {
       const int sel = comp == 0 ? SEL_RE : SEL_IM;
-      CK(launch_chunk_deltas(e->live, e->local_size, sel, res + RES_ZERO, e->ws, e->stream));
-      CK(launch_chunk_resolve(e->live, e->local_size, sel, res + RES_ZERO, e->ws, e->stream));
+      // (a Grover state is real: the imaginary parts' sum is skipped on the device when all are zero)
+      const long long *skip = comp == 1 ? e->ws.iresult + 2 : nullptr;
+      CK(launch_chunk_deltas(e->live, e->local_size, sel, res + RES_ZERO, e->ws, e->stream, skip));
+      CK(launch_chunk_resolve(e->live, e->local_size, sel, res + RES_ZERO, e->ws, e->stream, true, skip));
       CK(cudaMemcpyAsync(res + RES_SUM_RE + comp, res + RES_EXACT_TOTAL, sizeof(double),
                          cudaMemcpyDeviceToDevice, e->stream));
       e->kernel_launches += 5;

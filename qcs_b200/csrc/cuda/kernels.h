@@ -91,12 +91,18 @@ struct ReduceWorkspace {
   double *chunk_delta;     // device, n_chunks
   unsigned char *chunk_flag;  // device, n_chunks
   double *chunk_exact;     // device, n_chunks + 1
-  double *group_sum;       // device, n_chunks / 1024 + 1 (two-level resolve of large shards)
-  double *group_exact;     // device, n_chunks / 1024 + 1
-  unsigned char *group_flag;  // device, n_chunks / 1024 + 1
+  double *group_sum;       // device, n_chunks / QCS_RESOLVE_GROUP + 2 (two-level resolve of large shards)
+  double *group_exact;     // device, n_chunks / QCS_RESOLVE_GROUP + 2
+  unsigned char *group_flag;  // device, n_chunks / QCS_RESOLVE_GROUP + 2
   size_t n_chunks_cap;
 };
 enum { REDUCE_MAX_BLOCKS = 4096, SEQ_CHUNK = 1024 };
+// chunks per group of the two-level resolve.  Small groups: a group is walked chunk by chunk as soon
+// as ONE of its chunks is flagged or it spans a binade, and the one warp that walks pays ~1 us per 32
+// chunks -- with 1024-chunk groups the five binade crossings a 24-qubit Grover state has beyond its
+// first group cost 5 x 32 us per sum; the clean groups themselves cost ~20 cycles each (their records
+// are fetched 32 groups at a time).
+#define QCS_RESOLVE_GROUP 64
 // What the exact sequential sums add up (the `mask_pos` argument below): a position >= 0 = |a_i|^2 over
 // the indices with that bit clear, SEL_ALL = every |a_i|^2, SEL_RE / SEL_IM = the real / imaginary parts
 // of the amplitudes themselves (signed; q_apply_diffusion, reference src/q_gates.c:334-336).
@@ -150,12 +156,17 @@ cudaError_t launch_chunk_sums(const double2 *state, uint64_t n_amps, int mask_po
 // K1 for SEL_RE and SEL_IM in one read of the shard (no result[RES_APPROX_TOTAL])
 cudaError_t launch_chunk_sums_complex(const double2 *state, uint64_t n_amps, ReduceWorkspace &ws,
                                       cudaStream_t s);
+// skip_if_zero (may be null): device word that is 0 when every term is an exact zero
+// (launch_chunk_sums_complex leaves "some imaginary part is non-zero" in ws.iresult[2]): the kernels
+// return at once and the total is the start value.  total_only: the caller reads
+// result[RES_EXACT_TOTAL] and nothing else (chunk_exact[] is then not filled in for clean groups).
 cudaError_t launch_chunk_deltas(const double2 *state, uint64_t n_amps, int mask_pos,
                                 const double *approx_start_dev, ReduceWorkspace &ws,
-                                cudaStream_t s);
+                                cudaStream_t s, const long long *skip_if_zero = nullptr);
 cudaError_t launch_chunk_resolve(const double2 *state, uint64_t n_amps, int mask_pos,
                                  const double *exact_start_dev, ReduceWorkspace &ws,
-                                 cudaStream_t s);
+                                 cudaStream_t s, bool total_only = false,
+                                 const long long *skip_if_zero = nullptr);
 // Per shot: smallest i with u < running sum; -1 if none.  Needs launch_chunk_resolve first.
 cudaError_t launch_sample(const double2 *state, uint64_t n_amps, const ReduceWorkspace &ws,
                           const double *u_dev, int shots, long long *idx_dev,

@@ -413,7 +413,7 @@ chunk_sum_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mask_
 // of the real parts (sum_re, abs_re) and of the imaginary parts (sum_im, abs_im) per chunk.
 __global__ void __launch_bounds__(256)
 chunk_sum_complex_kernel(const double2 *__restrict__ state, uint64_t n_chunks, double *sum_re,
-                         double *abs_re, double *sum_im, double *abs_im) {
+                         double *abs_re, double *sum_im, double *abs_im, long long *im_nonzero) {
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -436,44 +436,50 @@ chunk_sum_complex_kernel(const double2 *__restrict__ state, uint64_t n_chunks, d
       sum_im[c] = si;
       abs_re[c] = ar;
       abs_im[c] = ai;
+      if (ai != 0.0) *im_nonzero = 1;  // (racing writers all store the same value)
     }
   }
 }
 
-// K2: approximate exclusive prefix over chunks (single block, 1024 threads).
+// K2: approximate exclusive prefix over chunks (single block, 1024 threads): coalesced tiles of 1024
+// chunk sums, a block-wide scan per tile (warp shuffles + one shared-memory hop), the running total
+// carried from tile to tile.  (The prefix is approximate by design -- any summation order will do.)
+// skip_if_zero (may be null): a device word that is 0 when every term of the sum is an exact zero
+// (chunk_sum_complex_kernel's "some imaginary part is non-zero" flag): nothing to do then.
 __global__ void __launch_bounds__(1024)
 chunk_scan_kernel(const double *chunk_sum, uint64_t n_chunks, const double *start_dev,
-                  double *approx) {
-  const double start = *start_dev;
-  __shared__ double sh[1024];
-  const uint64_t per = (n_chunks + 1023) / 1024;
-  const uint64_t lo = (uint64_t)threadIdx.x * per;
-  const uint64_t hi = lo + per < n_chunks ? lo + per : n_chunks;
-  double s = 0.0;
-  for (uint64_t c = lo; c < hi; c++) s += chunk_sum[c];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {  // exclusive scan of the 1024 partials by one warp: 32 per lane + a shuffle scan
-    double mine = 0.0;
-    for (int t = 0; t < 32; t++) mine += sh[threadIdx.x * 32 + t];
-    double incl = mine;
+                  double *approx, const long long *skip_if_zero) {
+  if (skip_if_zero && *skip_if_zero == 0) return;
+  __shared__ double warp_tot[32];
+  __shared__ double carry_sh;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double carry = *start_dev;
+  for (uint64_t base = 0; base < n_chunks; base += 1024) {
+    const uint64_t c = base + threadIdx.x;
+    const double v = c < n_chunks ? chunk_sum[c] : 0.0;
+    double incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const double v = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((int)threadIdx.x >= o) incl += v;
+      const double u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
     }
-    double run = start + (incl - mine);
-    for (int t = 0; t < 32; t++) {
-      const double v = sh[threadIdx.x * 32 + t];
-      sh[threadIdx.x * 32 + t] = run;
-      run += v;
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      const double t = warp_tot[lane];
+      double ti = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += u;
+      }
+      warp_tot[lane] = ti - t;  // exclusive over warps
+      if (lane == 31) carry_sh = ti;
     }
-  }
-  __syncthreads();
-  double run = sh[threadIdx.x];
-  for (uint64_t c = lo; c < hi; c++) {
-    approx[c] = run;
-    run += chunk_sum[c];
+    __syncthreads();
+    if (c < n_chunks) approx[c] = carry + warp_tot[w] + (incl - v);
+    carry += carry_sh;
+    __syncthreads();
   }
 }
 
@@ -483,7 +489,9 @@ chunk_scan_kernel(const double *chunk_sum, uint64_t n_chunks, const double *star
 __global__ void __launch_bounds__(128)
 chunk_delta_kernel(const double2 *__restrict__ state, uint64_t n_chunks, int mask_pos,
                    const double *__restrict__ chunk_sum, const double *__restrict__ approx,
-                   double *__restrict__ delta, unsigned char *__restrict__ flag) {
+                   double *__restrict__ delta, unsigned char *__restrict__ flag,
+                   const long long *skip_if_zero) {
+  if (skip_if_zero && *skip_if_zero == 0) return;  // every term is an exact zero (chunk_scan_kernel)
   // chunk_sum: what decides "this chunk adds nothing" -- the chunk's sum for non-negative terms, the
   // sum of magnitudes for signed ones (the launcher passes the right array)
   const bool is_signed = mask_pos <= SEL_RE;
@@ -586,12 +594,13 @@ __device__ __forceinline__ double replay_chunk(const double2 *__restrict__ state
 // of the approximate prefix; K4b walks the (few) groups, falling back to the per-chunk walk inside
 // marked groups or when the running sum leaves the binade; K4c fills the per-chunk running sums
 // of the clean groups in parallel (the sampler needs them).
-constexpr int RESOLVE_GROUP = 1024;
+constexpr int RESOLVE_GROUP = QCS_RESOLVE_GROUP;
 
 __global__ void __launch_bounds__(256)
 group_sum_kernel(const double *__restrict__ delta, const double *__restrict__ approx,
                  const unsigned char *__restrict__ flag, uint64_t n_chunks, uint64_t n_groups,
-                 double *__restrict__ gsum, unsigned char *__restrict__ gflag) {
+                 double *__restrict__ gsum, unsigned char *__restrict__ gflag, const long long *skip_if_zero) {
+  if (skip_if_zero && *skip_if_zero == 0) return;
   const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (g >= n_groups) return;
@@ -704,34 +713,87 @@ __device__ __forceinline__ double walk_chunks(const double2 *__restrict__ state,
   return S;
 }
 
-// K4b: one warp walks the groups; gexact[g] = running sum before group g, or NaN-free marker
-// gdone[g] = 1 when the per-chunk walk already wrote that group's chunk_exact entries.
+// K4b: one warp walks the groups; gexact[g] = running sum before group g, gflag[g] = 2 when the
+// per-chunk walk already wrote that group's chunk_exact entries.  The groups' records (flag, sum,
+// approximate prefix of the first chunk) are fetched 32 groups at a time, one per lane; a block of
+// 32 clean groups whose prefixes share the running sum's binade and whose sums share one sign is
+// one warp scan (the argument of walk_chunks' block shortcut, one level up: exact additions of
+// multiples of the binade's quantum, monotone, so the end point vouches for every step).
+// skip_if_zero: see chunk_scan_kernel -- the total is then the start value (adding exact zeros to it
+// changes nothing: the start is +0 or a non-zero running sum).
 __global__ void __launch_bounds__(32)
 group_resolve_kernel(const double2 *__restrict__ state, uint64_t n_chunks, uint64_t n_groups,
                      uint64_t chunk_len, int mask_pos, const double *start_dev,
                      const double *__restrict__ approx, const double *__restrict__ delta,
                      const unsigned char *__restrict__ flag, const double *__restrict__ gsum,
                      unsigned char *__restrict__ gflag, double *__restrict__ gexact,
-                     double *__restrict__ exact, double *total_out, long long *replays) {
+                     double *__restrict__ exact, double *total_out, long long *replays,
+                     const long long *skip_if_zero) {
   const int lane = threadIdx.x;
   double S = *start_dev;
-  long long n_replay = 0;
-  for (uint64_t g = 0; g < n_groups; g++) {
-    const uint64_t first = g * RESOLVE_GROUP;
-    const uint64_t last = first + RESOLVE_GROUP < n_chunks ? first + RESOLVE_GROUP : n_chunks;
-    bool clean = gflag[g] == 0 && same_binade(S, approx[first]);
-    double Snew = S;
-    if (clean) {
-      Snew = __dadd_rn(S, gsum[g]);
-      clean = same_binade(Snew, S);
+  if (skip_if_zero && *skip_if_zero == 0) {
+    if (lane == 0) {
+      *total_out = S;
+      if (replays) *replays = 0;
     }
-    if (lane == 0) gexact[g] = S;
-    if (clean) {
-      S = Snew;  // K4c fills this group's chunk_exact entries
-    } else {
-      S = walk_chunks(state, first, last, chunk_len, mask_pos, approx, delta, flag, 1, exact, S, lane,
-                      n_replay);
-      if (lane == 0) gflag[g] = 2;  // done here
+    return;
+  }
+  long long n_replay = 0;
+  for (uint64_t gb = 0; gb < n_groups; gb += 32) {
+    const uint64_t g_mine = gb + lane;
+    const bool have = g_mine < n_groups;
+    int my_gf = 1;
+    double my_gs = 0.0, my_ga = 0.0, my_gexact = 0.0;
+    if (have) {
+      my_gf = gflag[g_mine];
+      my_gs = gsum[g_mine];
+      my_ga = approx[g_mine * RESOLVE_GROUP];
+    }
+    const int lim = (int)((n_groups - gb) < 32 ? (n_groups - gb) : 32);
+    {
+      const unsigned bad = __ballot_sync(0xffffffffu, have && (my_gf != 0 || !same_binade(my_ga, S)));
+      const unsigned pos = __ballot_sync(0xffffffffu, have && my_gs > 0.0);
+      const unsigned neg = __ballot_sync(0xffffffffu, have && my_gs < 0.0);
+      if (bad == 0u && !(pos && neg)) {
+        const double dz = have ? my_gs : 0.0;
+        double incl = dz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const double Snew = __dadd_rn(S, __shfl_sync(0xffffffffu, incl, 31));
+        if (same_binade(Snew, S)) {
+          if (have) gexact[g_mine] = S + (incl - dz);
+          S = Snew;
+          continue;
+        }
+      }
+    }
+    for (int j = 0; j < lim; j++) {
+      const int gf = __shfl_sync(0xffffffffu, my_gf, j);
+      const double gs = __shfl_sync(0xffffffffu, my_gs, j);
+      const double ga = __shfl_sync(0xffffffffu, my_ga, j);
+      bool clean = gf == 0 && same_binade(S, ga);
+      double Snew = S;
+      if (clean) {
+        Snew = __dadd_rn(S, gs);
+        clean = same_binade(Snew, S);
+      }
+      if (lane == j) my_gexact = S;
+      if (clean) {
+        S = Snew;  // K4c fills this group's chunk_exact entries
+      } else {
+        const uint64_t first = (gb + (uint64_t)j) * RESOLVE_GROUP;
+        const uint64_t last = first + RESOLVE_GROUP < n_chunks ? first + RESOLVE_GROUP : n_chunks;
+        S = walk_chunks(state, first, last, chunk_len, mask_pos, approx, delta, flag, 1, exact, S, lane,
+                        n_replay);
+        if (lane == j) my_gf = 2;  // done here
+      }
+    }
+    if (have) {
+      gexact[g_mine] = my_gexact;
+      if (my_gf == 2) gflag[g_mine] = 2;
     }
   }
   if (lane == 0) {
@@ -775,8 +837,16 @@ chunk_resolve_kernel(const double2 *__restrict__ state, uint64_t n_amps, uint64_
                      uint64_t chunk_len, int mask_pos, const double *start_dev,
                      const double *__restrict__ approx, const double *__restrict__ delta,
                      const unsigned char *__restrict__ flag, int have_deltas,
-                     double *__restrict__ exact, double *total_out, long long *replays) {
+                     double *__restrict__ exact, double *total_out, long long *replays,
+                     const long long *skip_if_zero) {
   const int lane = threadIdx.x;
+  if (skip_if_zero && *skip_if_zero == 0) {
+    if (lane == 0) {
+      *total_out = *start_dev;
+      if (replays) *replays = 0;
+    }
+    return;
+  }
   long long n_replay = 0;
   const double S = walk_chunks(state, 0, n_chunks, chunk_len, mask_pos, approx, delta, flag,
                                have_deltas, exact, *start_dev, lane, n_replay);
@@ -930,36 +1000,40 @@ cudaError_t launch_chunk_sums(const double2 *state, uint64_t n, int mask_pos,
 }
 
 cudaError_t launch_chunk_sums_complex(const double2 *state, uint64_t n, ReduceWorkspace &ws, cudaStream_t s) {
-  if (n < (uint64_t)SEQ_CHUNK) return cudaSuccess;
+  // shards below one chunk have no chunk sums: the flag says "do not skip" (any non-zero bytes)
+  if (n < (uint64_t)SEQ_CHUNK) return cudaMemsetAsync(ws.iresult + 2, 1, sizeof(long long), s);
   const uint64_t n_chunks = n / SEQ_CHUNK;
   uint64_t blocks = (n_chunks + 7) / 8;
   if (blocks > (unsigned)device_sm_count() * 32) blocks = (unsigned)device_sm_count() * 32;
+  cudaError_t err = cudaMemsetAsync(ws.iresult + 2, 0, sizeof(long long), s);
+  if (err != cudaSuccess) return err;
   chunk_sum_complex_kernel<<<(unsigned)blocks, 256, 0, s>>>(state, n_chunks, ws.chunk_sum, ws.chunk_abs,
-                                                            ws.chunk_sum2, ws.chunk_abs2);
+                                                            ws.chunk_sum2, ws.chunk_abs2, ws.iresult + 2);
   return cudaGetLastError();
 }
 
 cudaError_t launch_chunk_deltas(const double2 *state, uint64_t n, int mask_pos,
                                 const double *approx_start_dev, ReduceWorkspace &ws,
-                                cudaStream_t s) {
+                                cudaStream_t s, const long long *skip_if_zero) {
   if (n < (uint64_t)SEQ_CHUNK) return cudaSuccess;
   const uint64_t n_chunks = n / SEQ_CHUNK;
-  chunk_scan_kernel<<<1, 1024, 0, s>>>(sums_of(ws, mask_pos), n_chunks, approx_start_dev, ws.chunk_approx);
+  chunk_scan_kernel<<<1, 1024, 0, s>>>(sums_of(ws, mask_pos), n_chunks, approx_start_dev, ws.chunk_approx,
+                                       skip_if_zero);
   const uint64_t groups = (n_chunks + 31) / 32;
   const uint64_t blocks = (groups + 3) / 4;
   chunk_delta_kernel<<<(unsigned)blocks, 128, 0, s>>>(state, n_chunks, mask_pos, zero_test_of(ws, mask_pos),
                                                       ws.chunk_approx, ws.chunk_delta,
-                                                      ws.chunk_flag);
+                                                      ws.chunk_flag, skip_if_zero);
   return cudaGetLastError();
 }
 
 cudaError_t launch_chunk_resolve(const double2 *state, uint64_t n, int mask_pos,
                                  const double *exact_start_dev, ReduceWorkspace &ws,
-                                 cudaStream_t s) {
+                                 cudaStream_t s, bool total_only, const long long *skip_if_zero) {
   if (n < (uint64_t)SEQ_CHUNK) {
     chunk_resolve_kernel<<<1, 32, 0, s>>>(state, n, 1, n, mask_pos, exact_start_dev, nullptr,
                                           nullptr, nullptr, 0, ws.chunk_exact,
-                                          ws.result + RES_EXACT_TOTAL, ws.iresult + 1);
+                                          ws.result + RES_EXACT_TOTAL, ws.iresult + 1, skip_if_zero);
     return cudaGetLastError();
   }
   const uint64_t n_chunks = n / SEQ_CHUNK;
@@ -967,19 +1041,23 @@ cudaError_t launch_chunk_resolve(const double2 *state, uint64_t n, int mask_pos,
     chunk_resolve_kernel<<<1, 32, 0, s>>>(state, n, n_chunks, SEQ_CHUNK, mask_pos, exact_start_dev,
                                           ws.chunk_approx, ws.chunk_delta, ws.chunk_flag, 1,
                                           ws.chunk_exact, ws.result + RES_EXACT_TOTAL,
-                                          ws.iresult + 1);
+                                          ws.iresult + 1, skip_if_zero);
     return cudaGetLastError();
   }
   const uint64_t n_groups = (n_chunks + RESOLVE_GROUP - 1) / RESOLVE_GROUP;
   const unsigned blocks = (unsigned)((n_groups + 7) / 8);  // 8 warps per block, one group per warp
   group_sum_kernel<<<blocks, 256, 0, s>>>(ws.chunk_delta, ws.chunk_approx, ws.chunk_flag, n_chunks,
-                                          n_groups, ws.group_sum, ws.group_flag);
+                                          n_groups, ws.group_sum, ws.group_flag, skip_if_zero);
   group_resolve_kernel<<<1, 32, 0, s>>>(state, n_chunks, n_groups, SEQ_CHUNK, mask_pos,
                                         exact_start_dev, ws.chunk_approx, ws.chunk_delta,
                                         ws.chunk_flag, ws.group_sum, ws.group_flag, ws.group_exact,
-                                        ws.chunk_exact, ws.result + RES_EXACT_TOTAL, ws.iresult + 1);
-  group_fill_kernel<<<blocks, 256, 0, s>>>(ws.chunk_delta, ws.chunk_flag, n_chunks, n_groups,
-                                           ws.group_flag, ws.group_exact, ws.chunk_exact);
+                                        ws.chunk_exact, ws.result + RES_EXACT_TOTAL, ws.iresult + 1,
+                                        skip_if_zero);
+  // the running sum in front of every chunk: what sampling and collapse read; a caller that wants the
+  // total alone (the diffusion mean) skips it
+  if (!total_only)
+    group_fill_kernel<<<blocks, 256, 0, s>>>(ws.chunk_delta, ws.chunk_flag, n_chunks, n_groups,
+                                             ws.group_flag, ws.group_exact, ws.chunk_exact);
   return cudaGetLastError();
 }
 
