@@ -63,9 +63,6 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__device__ __forceinline__ int exponent_of(double x) {
-  return (__double2hiint(x) >> 20) & 0x7ff;
-}
 // same sign and same binade (for the non-negative sums of |a|^2 this is the exponent test)
 __device__ __forceinline__ bool same_binade(double a, double b) {
   return (((unsigned)__double2hiint(a) ^ (unsigned)__double2hiint(b)) >> 20) == 0u;

@@ -214,7 +214,6 @@ struct PassBuilder {
     for (int p = 0; p < cfg.fixed_low; p++) tile.push_back(p);
   }
   bool has(int pos) const { return std::find(tile.begin(), tile.end(), pos) != tile.end(); }
-  bool empty() const { return gates.empty() && n_api == 0; }
 
   // one of the five lowest positions of the tile as it stands (a conservative stand-in for "lane
   // bit of the I/O segments": a lower position may still join the tile later)
