@@ -132,6 +132,31 @@ def test_qft30_plan_is_compact():
     assert all(p["api"] <= 240 for p in passes)     # QCS_MAX_PASS_GATES
 
 
+def test_tile_cap_search_keeps_the_smallest_tiles_that_need_no_more_passes():
+    """engine.cu plan_batch: a 30-qubit QFT needs 5 passes whether 11-bit tiles are allowed or not, so the
+    plan on 10-bit tiles wins (targets 10+5+5+5+5); a brickwork circuit needs fewer passes on 11-bit tiles
+    and keeps them; tile_search=off restores the greedy growth."""
+    for math in ("exact", "fast"):
+        on = _parse(_plan(30, [("qft",)], semantics="corrected", math=math)[0])
+        off = _parse(_plan(30, [("qft",)], semantics="corrected", math=math, tile_search="off")[0])
+        assert len(on) == len(off) == 5
+        assert all(len(p["tile"]) == 10 for p in on), [len(p["tile"]) for p in on]
+        assert any(len(p["tile"]) == 11 for p in off), [len(p["tile"]) for p in off]
+    script = po.random_circuit_script(30, 8)
+    on = _parse(_plan(30, script, semantics="corrected")[0])
+    small = _parse(_plan(30, script, semantics="corrected", tile_bits=10)[0])
+    assert len(on) < len(small) and any(len(p["tile"]) == 11 for p in on)
+
+
+def test_remap_buffer_option_is_validated():
+    from qcs_b200 import Circuit
+    from qcs_b200.circuit import QcsError
+    for ok in ("inplace", "auto"):
+        Circuit(12, dryrun=True, semantics="corrected", remap_buffer=ok).close()
+    with pytest.raises(QcsError):
+        Circuit(12, dryrun=True, semantics="corrected", remap_buffer="triple")
+
+
 def test_reference_semantics_cphase_is_a_value_noop():
     """As written in the reference a controlled phase changes no amplitude (defect D1): it is not scheduled."""
     text, st = _plan(14, [("h", 3), ("cphase", 1, 3, 0.4), ("cphase", 9, 3, 0.1), ("h", 8)],
