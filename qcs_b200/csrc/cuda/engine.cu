@@ -1343,7 +1343,7 @@ int qcs_cuda_diffusion(qcs_cuda_engine *e) {
       CK(launch_chunk_resolve(e->live, e->local_size, sel, res + RES_ZERO, e->ws, e->stream, true, skip));
       CK(cudaMemcpyAsync(res + RES_SUM_RE + comp, res + RES_EXACT_TOTAL, sizeof(double),
                          cudaMemcpyDeviceToDevice, e->stream));
-      e->kernel_launches += 5;
+      e->kernel_launches += 4;  // scan, deltas, group sums, walk (no per-chunk prefixes: total only)
     }
     e->algorithmic_bytes += 3 * 16.0 * (double)e->local_size;
   } else {
