@@ -99,6 +99,7 @@ static int load_options(Options &o) {
   o.fuse_swaps = !(v == "off" || v == "0");
   v = option_value("tile_search");
   o.tile_search = !(v == "off" || v == "0");
+  o.tile_search_heavy = o.tile_search && v != "caps";  // "caps": smaller caps only, FP64-heavy passes never grow
   v = option_value("fan_tables");
   // "off" | "on" | the fewest in-tile controls a run needs to become a table (on = 2)
   o.fan_tables = (v == "off" || v == "0") ? 0 : (v.empty() || v == "on") ? 2 : std::max(2, std::atoi(v.c_str()));
@@ -110,7 +111,8 @@ static int load_options(Options &o) {
   v = option_value("victim_policy");
   if (v == "lru") o.victim_policy = 0;
   else if (v.empty() || v == "mru") o.victim_policy = 1;
-  else return set_error(QCS_CUDA_ERR_INVALID, "victim_policy must be mru|lru, got '%s'", v.c_str());
+  else if (v == "mru2") o.victim_policy = 2;  // experimental: mru, but not from the last pass in front of the remap
+  else return set_error(QCS_CUDA_ERR_INVALID, "victim_policy must be mru|lru|mru2, got '%s'", v.c_str());
   v = option_value("remap_max");
   if (!v.empty()) o.remap_max = std::atoi(v.c_str());
   if (o.remap_max < 1 || o.remap_max > QCS_MAX_REMAP) o.remap_max = Options().remap_max;
@@ -391,13 +393,25 @@ static std::vector<PassPlan> plan_batch(const Engine &e, const std::vector<PhysG
   // 10+5+5+5+5 on 10-bit tiles against 11+6+6+6+1 with 11 allowed -- 62.3 vs 63.6 ms bit-exact, 34.4 vs
   // 36.4 ms fast; the random circuits keep their 11-bit plans, which are passes shorter).  Planning is
   // repeated once per smaller cap, so only for queues where that is cheap.
-  if (e.opt.tile_search && gates.size() <= 1024)
+  if (e.opt.tile_search && gates.size() <= 1024) {
     for (int cap = cfg.tile_bits_max - 1; cap >= cfg.tile_bits_min; cap--) {
       PlannerConfig smaller = cfg;
       smaller.tile_bits_max = cap;
       std::vector<PassPlan> alt = plan_passes(gates, smaller);
       if (alt.size() <= best.size()) best.swap(alt);
     }
+    // ... and FP64-heavy passes stay on the smallest tiles (compute_bound_flops) unless letting them
+    // grow saves a whole pass: a 31..33-qubit QFT shard needs 10 + 5 + 5 + 5 + 5 + 1 targets' worth of
+    // passes on 10-bit tiles and 10 + 6 + 6 + 6 + 3 with 11 allowed
+    if (!cfg.fast_math && e.opt.tile_search_heavy)
+      for (int cap = cfg.tile_bits_max; cap > cfg.tile_bits_min; cap--) {
+        PlannerConfig heavy = cfg;
+        heavy.tile_bits_max = cap;
+        heavy.compute_bound_flops = 1e30;
+        std::vector<PassPlan> alt = plan_passes(gates, heavy);
+        if (alt.size() < best.size()) best.swap(alt);
+      }
+  }
   return best;
 }
 
@@ -547,8 +561,13 @@ struct VictimRanking {
   std::vector<long> next_use;   // per position (local AND global): queue index of the next pairing use at or
                                 // after `from` of the qubit sitting there, q.size() + 1 if none
 };
+// mru_before: among positions the queue never pairs again, one last paired at or after this queue index
+// ranks behind the others (run_range passes the first gate of the LAST pass in front of the remap: a
+// victim paired there pins the remap to that pass, and the gate that needed the remap -- often the
+// last of a QFT -- then gets a pass of its own; a victim from the pass before lets the last pass be
+// planned again behind the remap, with that gate in it).
 static VictimRanking rank_victims(const Engine &e, const std::vector<HostGate> &q, size_t from, size_t since,
-                                  int lowest) {
+                                  int lowest, long mru_before = -1) {
   VictimRanking vr;
   vr.next_use.assign(e.n, (long)q.size() + 1);
   std::vector<long> last_use(e.n, -1);
@@ -567,12 +586,16 @@ static VictimRanking rank_victims(const Engine &e, const std::vector<HostGate> &
   // repeated QFT a second remap per round, stand-alone at that: nothing runs before the first gate of
   // the next round for it to ride on); then positions every tile contains (only offered when
   // lowest < 5: whatever arrives there is pairable in every later pass); then the highest.
-  const bool mru = e.opt.victim_policy == 1;
+  const bool mru = e.opt.victim_policy >= 1;
   std::stable_sort(vr.order.begin(), vr.order.end(), [&](int a, int b) {
     if (vr.next_use[a] != vr.next_use[b]) return vr.next_use[a] > vr.next_use[b];
     if (last_use[a] != last_use[b]) {
       if (!mru) return last_use[a] < last_use[b];
       if ((last_use[a] < 0) != (last_use[b] < 0)) return last_use[a] < 0;
+      if (mru_before >= 0) {
+        const bool late_a = last_use[a] >= mru_before, late_b = last_use[b] >= mru_before;
+        if (late_a != late_b) return late_b;
+      }
       return last_use[a] > last_use[b];
     }
     return (a < QCS_LANE_BITS) && !(b < QCS_LANE_BITS);
@@ -719,7 +742,19 @@ static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, si
     }
     if (x == end) return run_local(e, batch);
     const int gpos = e.perm[q[x].target];
-    const VictimRanking vr = rank_victims(e, q, x, i, fuse ? e.opt.min_fused_victim : QCS_LANE_BITS);
+    std::vector<PassPlan> plan;
+    long last_pass_from = -1;  // queue index of the first gate of the batch plan's last pass
+    if (fuse) {
+      plan = plan_batch(e, batch);
+      if (plan.size() > 1) {
+        last_pass_from = (long)i;
+        for (size_t k = 0; k + 1 < plan.size(); k++) last_pass_from += plan[k].n_gates_api;
+      }
+    }
+    // (victim_policy=mru2: see rank_victims; measured in the planner only -- on 8 ranks the layouts it leaves
+    // behind cost a second carrying pass in two QFT steps out of five)
+    const VictimRanking vr = rank_victims(e, q, x, i, fuse ? e.opt.min_fused_victim : QCS_LANE_BITS,
+                                          e.opt.victim_policy == 2 ? last_pass_from : -1);
     const int victim = vr.order[0];
     if (!fuse) {
       RC(run_local(e, batch));
@@ -758,7 +793,6 @@ static int run_range(Engine &e, const std::vector<HostGate> &q, size_t begin, si
       if (is_pairing_kind(batch[k - i].c.kind))
         for (int j = 0; j < k_pairs; j++)
           if (batch[k - i].tpos == lpos_k[j]) legal_from = k + 1;
-    std::vector<PassPlan> plan = plan_batch(e, batch);
     size_t pass_end = i, chosen = plan.size();
     for (size_t k = 0; k < plan.size(); k++) {
       pass_end += (size_t)plan[k].n_gates_api;

@@ -36,6 +36,7 @@ struct Options {
   bool peephole = true;    // drop exactly self-cancelling gate pairs from the queue (corrected semantics)
   bool fuse_swaps = true;  // fold position swaps into the stores of a pass (peer-memory path only)
   bool tile_search = true;  // plan again with smaller tile caps and keep the smallest that needs no more passes
+  bool tile_search_heavy = true;  // ... and with FP64-heavy passes allowed to grow, kept when it saves a pass
   int fan_tables = 2;  // math=fast: runs of controlled phases with at least this many in-tile controls become
                        // per-thread tables (0 = never)
   int victim_policy = 1;   // which local position leaves when the queue pairs none of the candidates again:

@@ -1,4 +1,4 @@
-"""Swap-carrying passes: TMA bulk stores vs 16-byte stores, per pass (development aid; run under torchrun):
+"""Swap-carrying passes: TMA bulk stores vs 16-byte stores, per pass, or one configuration given as option=value,... (development aid; run under torchrun):
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/r2_swap_bw.py [local_qubits]"""
 import ctypes, math, os, sys
 import torch
@@ -45,9 +45,15 @@ def run(script, label, reps=2, **kw):
     c.close()
 
 
-for store in ("bulk", "thread"):
-    for math_ in ("exact", "fast"):
-        run([("qft",)], f"qft {math_}/{store}", math=math_, swap_store=store)
-        run(po.random_circuit_script(n, 8), f"random_d8 {math_}/{store}", reps=1, math=math_, swap_store=store)
+extra = dict(kv.split("=") for kv in sys.argv[2].split(",")) if len(sys.argv) > 2 and sys.argv[2] else {}
+if extra:   # one configuration, bit-exact only: r2_swap_bw.py 30 compute_bound_flops=1e9
+    tag = ",".join(f"{k}={v}" for k, v in extra.items())
+    run([("qft",)], f"qft exact {tag}", reps=4, **extra)
+    run(po.random_circuit_script(n, 8), f"random_d8 exact {tag}", reps=1, **extra)
+else:
+    for store in ("bulk", "thread"):
+        for math_ in ("exact", "fast"):
+            run([("qft",)], f"qft {math_}/{store}", math=math_, swap_store=store)
+            run(po.random_circuit_script(n, 8), f"random_d8 {math_}/{store}", reps=1, math=math_, swap_store=store)
 C.qcs_cuda_dist_finalize()
 dist.destroy_process_group()
